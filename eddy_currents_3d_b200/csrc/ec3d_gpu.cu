@@ -1,0 +1,1155 @@
+// ec3d_gpu.cu -- C ABI (include/ec3d_gpu.h) and host runtime of libec3d_gpu.so.
+//
+// Host side of the hot path: coefficient tables, z-slab layout, launch sequencing of the
+// BiCGSTABwr iteration (device-resident scalars, no host round trip inside an iteration, CUDA
+// graph of iteration chunks on one GPU), NCCL halo exchange + scalar all-reduces across slabs, and
+// the timestep body of the reference's main loop (EC3D.f90:275-433).
+#include "../../include/ec3d_gpu.h"
+#include "ec3d_assembly.cuh"
+#include "ec3d_common.cuh"
+#include "ec3d_kernels.cuh"
+#include "ec3d_step.cuh"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------
+// errors, counters
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void ec3d_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *ec3d_last_error(void) { return g_err; }
+extern "C" const char *ec3d_version(void) { return "ec3d_gpu 0.1 (sm_100a)"; }
+extern "C" int64_t ec3d_global_launch_count(void) { return g_launches.load(); }
+
+#define NCCL_TRY(expr)                                                                       \
+    do {                                                                                     \
+        ncclResult_t _r = (expr);                                                            \
+        if (_r != ncclSuccess) {                                                             \
+            ec3d_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, ncclGetErrorString(_r)); \
+            return EC3D_ERR_NCCL;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define LAUNCHED(ctr) do { ++(ctr); g_launches.fetch_add(1, std::memory_order_relaxed); } while (0)
+
+// ------------------------------------------------------------------------------------------
+// coefficient tables -- expression shapes follow the reference literally (this file is compiled
+// with -ffp-contract=off for the host so nothing is fused)
+// ------------------------------------------------------------------------------------------
+static void build_coef(const double delta[3], double dt, const double BND[3][2], Coef &c)
+{
+    const double sz = 1.0 / (delta[2] * delta[2]);          // EC3D.f90:496-498
+    const double sy = 1.0 / (delta[1] * delta[1]);
+    const double sx = 1.0 / (delta[0] * delta[0]);
+    const double s[3] = {sx, sy, sz};
+    c.msx = -sx; c.msy = -sy; c.msz = -sz;
+    for (int a = 0; a < 3; ++a) {
+        c.blo[a] = BND[a][1] * s[a];                        // low face:  BND(a,2)*s on the '+' neighbour
+        c.bhi[a] = BND[a][0] * s[a];                        // high face: BND(a,1)*s on the '-' neighbour
+        c.m2s[a] = -2.0 * s[a];
+        c.ua_m[a] = 0.5 / dt * (-1.0 / delta[a]);           // EC3D.f90:921
+        c.ua_p[a] = 0.5 / dt * (1.0 / delta[a]);
+        c.uc_m[a] = -2.0 / (dt * delta[a]);                 // EC3D.f90:774 ff
+        c.uc_p[a] = +2.0 / (dt * delta[a]);
+    }
+    c.diag_int = 2.0 * (sx + sy + sz);                      // EC3D.f90:651
+    for (int m = 0; m < 8; ++m) {                           // EC3D.f90:533-642, e.g. (2.d0*sx + sy + sz)
+        const double tx = (m & 1) ? sx : 2.0 * sx;
+        const double ty = (m & 2) ? sy : 2.0 * sy;
+        const double tz = (m & 4) ? sz : 2.0 * sz;
+        c.diag_b[m] = tx + ty + tz;
+    }
+}
+
+static void build_matcoef(const double delta[3], double dt, const double *vp /* valPHYS row */, MatCoef &m)
+{
+    const double sz = 1.0 / (delta[2] * delta[2]);
+    const double sy = 1.0 / (delta[1] * delta[1]);
+    const double sx = 1.0 / (delta[0] * delta[0]);
+    const double s[3] = {sx, sy, sz};
+    const double C = vp[1];
+    for (int a = 0; a < 3; ++a) {
+        const double ds = 0.5 / delta[a];                   // EC3D.f90:499-501
+        m.cm[a] = -s[a] - vp[2 + a] / (2.0 * delta[a]);     // EC3D.f90:657-662
+        m.cp[a] = -s[a] + vp[2 + a] / (2.0 * delta[a]);
+        m.g1[a] = C * ds;                                   // EC3D.f90:667-710
+        m.g3[a] = 3.0 * C * ds;
+        m.g4[a] = 4.0 * C * ds;
+    }
+    m.diag = 2.0 * (sx + sy + sz) + 2.0 * C / dt;           // EC3D.f90:663
+}
+
+// ------------------------------------------------------------------------------------------
+// host-only: weighted slab partition
+// ------------------------------------------------------------------------------------------
+extern "C" int ec3d_partition_planes(int32_t sdx, int32_t sdy, int32_t sdz, const int64_t *cond_per_plane,
+                                     int32_t nranks, int32_t *kstart)
+{
+    if (nranks < 1 || sdz < 2 * nranks || !kstart) { ec3d_set_error("partition: need sdz >= 2*nranks"); return EC3D_ERR_ARG; }
+    // bytes one BiCGSTABwr iteration moves per plane: 19 vector passes over 3 A unknowns per cell
+    // and 1 U unknown per conductor cell, plus the geoPHYS_C map read by the two SpMVs
+    const double kdz = (double)sdx * sdy;
+    std::vector<double> w(sdz), cum(sdz + 1, 0.0);
+    for (int k = 0; k < sdz; ++k) {
+        const double nc = cond_per_plane ? (double)cond_per_plane[k] : 0.0;
+        w[k] = 152.0 * (3.0 * kdz + nc) + 2.0 * 4.0 * kdz + 120.0 * nc;
+        cum[k + 1] = cum[k] + w[k];
+    }
+    kstart[0] = 0;
+    for (int r = 1; r < nranks; ++r) {
+        const double target = cum[sdz] * r / nranks;
+        int k = kstart[r - 1] + 2;
+        while (k < sdz - 2 * (nranks - r) && cum[k] < target) ++k;
+        // pick the closer of k-1 / k
+        if (k - 1 >= kstart[r - 1] + 2 && std::fabs(cum[k - 1] - target) < std::fabs(cum[k] - target)) --k;
+        kstart[r] = k;
+    }
+    kstart[nranks] = sdz;
+    return EC3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic BiCGSTABwr driver over "an SpMV + a segmented vector layout"
+// ------------------------------------------------------------------------------------------
+struct Solver {
+    SlabGeom G{};
+    cudaStream_t st = nullptr;
+    Scal *sc = nullptr;
+    int *iter_base = nullptr;
+    double *partials = nullptr;
+    int pstride = 0;
+    double *X = nullptr, *R = nullptr, *R0 = nullptr, *P = nullptr, *AP = nullptr, *S = nullptr, *AS = nullptr;
+    int nblkVec = 1, vec = 1;
+    // launches the SpMV kernel(s) for `mode`; returns kernels launched
+    std::function<int(int mode, const VecSet &vs, const IterCtl &ctl)> spmv;
+    std::function<int(double *v)> halo;                 // refresh halo entries of v (nranks > 1)
+    std::function<int(int slot, int count)> allreduce;  // sum sc->red[slot..slot+count) over ranks
+    bool multi = false;
+    // graph of `graph_chunk` iterations (single rank only)
+    cudaGraphExec_t graph = nullptr;
+    int graph_chunk = 0;
+    long long graph_launches = 0;                       // kernels inside one graph launch
+    int *h_flags = nullptr;                             // pinned: [done, final_iter, exit_kind, restarts]
+    long long launches = 0, iterations = 0;
+    int last_exit_kind = 0, last_restarts = 0;
+    double last_resid = 0.0;
+    int predicted = 0;                                  // iteration count of the previous solve
+};
+
+static int solver_enqueue_iteration(Solver &s, int it_off)
+{
+    const SlabGeom &G = s.G;
+    const IterCtl ctl{s.sc, s.iter_base, it_off};
+    const unsigned nb = (unsigned)s.nblkVec;
+    if (s.multi) { int rc = s.halo(s.P); if (rc) return rc; }
+    {   // AP = A*P, (AP,R0)                                        solvers.f90:30-32
+        VecSet vs{s.P, s.AP, s.R0, nullptr, nullptr, nullptr, nullptr};
+        s.launches += s.spmv(MODE_AP, vs, ctl);
+    }
+    if (s.multi) { int rc = s.allreduce(RED_APR0, 1); if (rc) return rc; }
+    if (s.vec == 2) k_s_update<2><<<nb, 256, 0, s.st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
+    else            k_s_update<1><<<nb, 256, 0, s.st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
+    LAUNCHED(s.launches);
+    if (s.multi) { int rc = s.allreduce(RED_SS, 1); if (rc) return rc; rc = s.halo(s.S); if (rc) return rc; }
+    {   // AS = A*S, (AS,S), (AS,AS)                                solvers.f90:39-40
+        VecSet vs{s.S, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr};
+        s.launches += s.spmv(MODE_AS, vs, ctl);
+    }
+    if (s.multi) { int rc = s.allreduce(RED_ASS, 2); if (rc) return rc; }
+    if (s.vec == 2) k_xr_update<2><<<nb, 256, 0, s.st>>>(G, s.X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
+    else            k_xr_update<1><<<nb, 256, 0, s.st>>>(G, s.X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
+    LAUNCHED(s.launches);
+    if (s.multi) { int rc = s.allreduce(RED_RR, 2); if (rc) return rc; }
+    if (s.vec == 2) k_p_update<2><<<nb, 256, 0, s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
+    else            k_p_update<1><<<nb, 256, 0, s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
+    LAUNCHED(s.launches);
+    return EC3D_OK;
+}
+
+static int solver_build_graph(Solver &s, int chunk)
+{
+    if (s.multi || chunk <= 0) return EC3D_OK;
+    cudaGraph_t g = nullptr;
+    const long long before = s.launches;
+    const long long gbefore = g_launches.load();
+    CUDA_TRY(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
+    for (int q = 1; q <= chunk; ++q) solver_enqueue_iteration(s, q);
+    k_iter_advance<<<1, 1, 0, s.st>>>(s.iter_base, chunk);
+    CUDA_TRY(cudaStreamEndCapture(s.st, &g));
+    CUDA_TRY(cudaGraphInstantiate(&s.graph, g, 0));
+    CUDA_TRY(cudaGraphDestroy(g));
+    s.graph_chunk = chunk;
+    s.graph_launches = (s.launches - before) + 1;
+    s.launches = before;                 // capture does not execute anything
+    g_launches.store(gbefore);
+    return EC3D_OK;
+}
+
+// B is the right-hand side (local layout), s.X the initial guess / result.
+static int solver_run(Solver &s, const double *B, double tol, int itmax, int *iter)
+{
+    k_solver_reset<<<1, 1, 0, s.st>>>(s.sc, s.iter_base, tol, itmax);
+    LAUNCHED(s.launches);
+    if (s.multi) { int rc = s.halo(s.X); if (rc) return rc; }
+    {   // R = B - A*X; R0 = R; P = R; ||b||^2; (R,R0)               solvers.f90:13-21
+        VecSet vs{s.X, nullptr, nullptr, B, s.R, s.R0, s.P};
+        const IterCtl ctl{s.sc, s.iter_base, 0};
+        s.launches += s.spmv(MODE_INIT, vs, ctl);
+    }
+    if (s.multi) { int rc = s.allreduce(RED_BB, 2); if (rc) return rc; }
+    const long long cap = (long long)itmax + 2;       // the reference runs at most itmax+1 iterations
+    long long enq = 0;
+    int chunk = s.graph ? s.graph_chunk : 8;
+    // first burst: as many chunks as the previous solve needed (warm-started steps are similar)
+    long long burst = std::max<long long>(chunk, ((long long)s.predicted / chunk) * chunk);
+    for (;;) {
+        long long todo = std::min(burst, std::max<long long>(cap - enq, 0));
+        if (todo <= 0) todo = chunk;                   // guards only: kernels exit on iter > itmax
+        for (long long d = 0; d < todo; d += chunk) {
+            if (s.graph) {
+                CUDA_TRY(cudaGraphLaunch(s.graph, s.st));
+                s.launches += s.graph_launches;
+                g_launches.fetch_add(s.graph_launches);
+            } else {
+                for (int q = 1; q <= chunk; ++q) { int rc = solver_enqueue_iteration(s, q); if (rc) return rc; }
+                k_iter_advance<<<1, 1, 0, s.st>>>(s.iter_base, chunk);
+                LAUNCHED(s.launches);
+            }
+            enq += chunk;
+        }
+        CUDA_TRY(cudaMemcpyAsync(s.h_flags, &s.sc->done, 4 * sizeof(int), cudaMemcpyDeviceToHost, s.st));
+        CUDA_TRY(cudaStreamSynchronize(s.st));
+        if (s.h_flags[0]) break;
+        burst = chunk;
+    }
+    *iter = s.h_flags[1];
+    s.last_exit_kind = s.h_flags[2];
+    s.last_restarts = s.h_flags[3];
+    s.iterations += *iter;
+    s.predicted = *iter;
+    if (s.last_exit_kind == 3) {
+        // IF (iter > itmax) THEN; PRINT*, norm2(R)   (solvers.f90:25-27)
+        double red[8];
+        CUDA_TRY(cudaMemcpy(red, s.sc->red, sizeof(red), cudaMemcpyDeviceToHost));
+        s.last_resid = std::sqrt(red[RED_RR]);
+        printf(" %24.16E\n", s.last_resid);
+        fflush(stdout);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return EC3D_OK;
+}
+
+static void flat_geom(long long n, SlabGeom &G)
+{
+    memset(&G, 0, sizeof(G));
+    G.own_off[0] = 0; G.own_len[0] = n;
+    G.own_cum[0] = 0; G.own_cum[1] = G.own_cum[2] = G.own_cum[3] = G.own_cum[4] = n;
+    G.n_own = n; G.ltot = n;
+}
+
+static int vec_blocks(long long n_own, int vec)
+{
+    long long units = n_own / vec;
+    long long b = (units + 256 * 4 - 1) / (256 * 4);
+    return (int)std::max<long long>(1, std::min<long long>(b, 148 * 8));
+}
+
+// ------------------------------------------------------------------------------------------
+// 1. strict drop-in: CSR BiCGSTABwr with a cached device copy of the matrix
+// ------------------------------------------------------------------------------------------
+struct CsrCache {
+    const void *hval = nullptr, *hirow = nullptr, *hjcol = nullptr;
+    int n = 0; long long nnz = 0; int first_irow = 0, last_jcol = 0; double first_val = 0.0;
+    int *irow = nullptr, *jcol = nullptr; double *val = nullptr;
+    double *vecs = nullptr;     // 8 vectors of n: X,B,R,R0,P,AP,S,AS
+    Solver sol;
+    cudaStream_t st = nullptr;
+    bool ready = false;
+    void release()
+    {
+        if (sol.graph) cudaGraphExecDestroy(sol.graph);
+        sol.graph = nullptr;
+        cudaFree(irow); cudaFree(jcol); cudaFree(val); cudaFree(vecs);
+        cudaFree(sol.sc); cudaFree(sol.iter_base); cudaFree(sol.partials);
+        if (sol.h_flags) cudaFreeHost(sol.h_flags);
+        if (st) cudaStreamDestroy(st);
+        *this = CsrCache();
+    }
+};
+static CsrCache g_csr;
+static std::mutex g_csr_mu;
+
+extern "C" void ec3d_csr_cache_clear(void)
+{
+    std::lock_guard<std::mutex> lk(g_csr_mu);
+    if (g_csr.ready || g_csr.irow) g_csr.release();
+}
+
+static int csr_prepare(const double *valA, const int32_t *irow, const int32_t *jcol, int32_t n)
+{
+    const long long nnz = (long long)irow[n] - 1;
+    CsrCache &c = g_csr;
+    if (c.ready && c.hval == valA && c.hirow == irow && c.hjcol == jcol && c.n == n && c.nnz == nnz &&
+        c.first_irow == irow[1] && c.last_jcol == jcol[nnz - 1] && c.first_val == valA[0])
+        return EC3D_OK;
+    if (c.ready || c.irow) c.release();
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) { ec3d_set_error("no CUDA device"); return EC3D_ERR_CUDA; }
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&c.irow, (size_t)(n + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c.jcol, (size_t)nnz * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c.val, (size_t)nnz * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.vecs, (size_t)n * 8 * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c.irow, irow, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, c.st));
+    CUDA_TRY(cudaMemcpyAsync(c.jcol, jcol, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, c.st));
+    CUDA_TRY(cudaMemcpyAsync(c.val, valA, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, c.st));
+    Solver &s = c.sol;
+    flat_geom(n, s.G);
+    s.st = c.st;
+    CUDA_TRY(cudaMalloc(&s.sc, sizeof(Scal)));
+    CUDA_TRY(cudaMalloc(&s.iter_base, sizeof(int)));
+    const int nblk = (n + 255) / 256;
+    s.vec = (n % 2 == 0) ? 2 : 1;
+    s.nblkVec = vec_blocks(n, s.vec);
+    s.pstride = std::max(nblk, s.nblkVec);
+    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 2 * sizeof(double)));
+    CUDA_TRY(cudaHostAlloc(&s.h_flags, 4 * sizeof(int), cudaHostAllocDefault));
+    double *v = c.vecs;
+    s.X = v; s.R = v + 2LL * n; s.R0 = v + 3LL * n; s.P = v + 4LL * n; s.AP = v + 5LL * n; s.S = v + 6LL * n;
+    s.AS = v + 7LL * n;
+    const int *dirow = c.irow, *djcol = c.jcol;
+    const double *dval = c.val;
+    Solver *sp = &s;
+    s.spmv = [=](int mode, const VecSet &vs, const IterCtl &ctl) -> int {
+        const unsigned nb = (unsigned)nblk;
+        switch (mode) {
+        case MODE_AP:   k_csr_spmv<MODE_AP><<<nb, 256, 0, sp->st>>>(n, dirow, djcol, dval, vs, ctl, sp->partials, sp->pstride, nb); break;
+        case MODE_AS:   k_csr_spmv<MODE_AS><<<nb, 256, 0, sp->st>>>(n, dirow, djcol, dval, vs, ctl, sp->partials, sp->pstride, nb); break;
+        case MODE_INIT: k_csr_spmv<MODE_INIT><<<nb, 256, 0, sp->st>>>(n, dirow, djcol, dval, vs, ctl, sp->partials, sp->pstride, nb); break;
+        default:        k_csr_spmv<MODE_PLAIN><<<nb, 256, 0, sp->st>>>(n, dirow, djcol, dval, vs, ctl, sp->partials, sp->pstride, nb); break;
+        }
+        g_launches.fetch_add(1);
+        return 1;
+    };
+    s.multi = false;
+    const char *ge = getenv("EC3D_GRAPH");
+    if (!ge || atoi(ge) != 0) { int rc = solver_build_graph(s, 8); if (rc) return rc; }
+    c.hval = valA; c.hirow = irow; c.hjcol = jcol; c.n = n; c.nnz = nnz;
+    c.first_irow = irow[1]; c.last_jcol = jcol[nnz - 1]; c.first_val = valA[0];
+    c.ready = true;
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_bicgstabwr_csr(const double *valA, const int32_t *irow, const int32_t *jcol, int32_t n,
+                                   const double *b, double *x, double tolerance, int32_t itmax, int32_t *iter)
+{
+    if (!valA || !irow || !jcol || !b || !x || !iter || n <= 0) { ec3d_set_error("bad argument"); return EC3D_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(g_csr_mu);
+    int rc = csr_prepare(valA, irow, jcol, n);
+    if (rc) return rc;
+    CsrCache &c = g_csr;
+    Solver &s = c.sol;
+    double *dB = c.vecs + (long long)n;
+    CUDA_TRY(cudaMemcpyAsync(s.X, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.st));
+    CUDA_TRY(cudaMemcpyAsync(dB, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.st));
+    rc = solver_run(s, dB, tolerance, itmax, iter);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(x, s.X, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.st));
+    CUDA_TRY(cudaStreamSynchronize(c.st));
+    return EC3D_OK;
+}
+
+extern "C" void sprsbcgstabwr_(double *valA, int32_t *irow, int32_t *jcol, int32_t *n, double *b, double *x,
+                               double *tolerance, int32_t *itmax, int32_t *iter)
+{
+    int rc = ec3d_bicgstabwr_csr(valA, irow, jcol, *n, b, x, *tolerance, *itmax, iter);
+    if (rc != EC3D_OK) {
+        fprintf(stderr, "sprsbcgstabwr_ (GPU): error %d: %s\n", rc, ec3d_last_error());
+        *iter = -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. GPU-resident handle
+// ------------------------------------------------------------------------------------------
+struct ec3d_handle {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    SlabGeom G{};
+    Coef cf{};
+    int nmat = 0;
+    MatCoef *d_mc = nullptr;
+    int *d_geo = nullptr;
+    signed char *d_mat = nullptr;
+    int *d_cond_cells = nullptr;
+    int ncond = 0;
+    unsigned char *d_flags = nullptr;
+    double valdom = 0.0;
+    int size_PHYS_C = 0;
+    double dt = 0.0, delta[3] = {0, 0, 0}, tol = 0.0;
+    int itmax = 0;
+    long long nCells0 = 0, nGlob = 0;
+    // vectors (local layout)
+    double *vecs = nullptr;
+    double *Uaf = nullptr, *Jaf = nullptr, *tmpx = nullptr, *tmpy = nullptr;
+    Solver sol;
+    // sources
+    int numfun = 0, numMech = 0, flag_move = 0, total_nodes = 0;
+    std::vector<int> h_nod_ptr, h_comp;
+    int *d_nod_ptr = nullptr, *d_nods = nullptr, *d_num_Vmech = nullptr, *d_comp = nullptr, *d_new_nodes = nullptr;
+    MotionState *d_ms = nullptr;
+    double *d_fun_vely = nullptr, *d_vmech = nullptr;
+    double *h_src = nullptr;     // pinned staging for the per-step scalars
+    int *d_oob = nullptr;
+    // launch configuration
+    int zc = 1;
+    dim3 airGrid;
+    int nblkAir = 0, nblkCond = 0;
+    // multi-GPU
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    long long nU_send_lo = 0, nU_send_hi = 0;   // U entries in my first / last two planes
+    // timing
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double last_step_ms = 0.0, last_solve_ms = 0.0;
+    long long launches = 0;
+};
+
+static int h_halo(ec3d_handle *h, double *v)
+{
+    if (h->nranks == 1) return EC3D_OK;
+    const SlabGeom &G = h->G;
+    const long long kdz = G.kdz;
+    NCCL_TRY(ncclGroupStart());
+    if (h->rank > 0) {
+        const int peer = h->rank - 1;
+        for (int c = 0; c < 3; ++c) {
+            NCCL_TRY(ncclSend(v + c * G.segA + kdz, kdz, ncclDouble, peer, h->comm, h->st));
+            NCCL_TRY(ncclRecv(v + c * G.segA, kdz, ncclDouble, peer, h->comm, h->st));
+        }
+        if (h->nU_send_lo) NCCL_TRY(ncclSend(v + G.offU + G.nUlo, h->nU_send_lo, ncclDouble, peer, h->comm, h->st));
+        if (G.nUlo) NCCL_TRY(ncclRecv(v + G.offU, G.nUlo, ncclDouble, peer, h->comm, h->st));
+    }
+    if (h->rank < h->nranks - 1) {
+        const int peer = h->rank + 1;
+        for (int c = 0; c < 3; ++c) {
+            NCCL_TRY(ncclSend(v + c * G.segA + (long long)G.nzl * kdz, kdz, ncclDouble, peer, h->comm, h->st));
+            NCCL_TRY(ncclRecv(v + c * G.segA + (long long)(G.nzl + 1) * kdz, kdz, ncclDouble, peer, h->comm, h->st));
+        }
+        if (h->nU_send_hi)
+            NCCL_TRY(ncclSend(v + G.offU + G.nUlo + G.nUown - h->nU_send_hi, h->nU_send_hi, ncclDouble, peer, h->comm, h->st));
+        if (G.nUhi) NCCL_TRY(ncclRecv(v + G.offU + G.nUlo + G.nUown, G.nUhi, ncclDouble, peer, h->comm, h->st));
+    }
+    NCCL_TRY(ncclGroupEnd());
+    return EC3D_OK;
+}
+
+static int h_allreduce(ec3d_handle *h, int slot, int count)
+{
+    if (h->nranks == 1) return EC3D_OK;
+    NCCL_TRY(ncclAllReduce(h->sol.sc->red + slot, h->sol.sc->red + slot, count, ncclDouble, ncclSum, h->comm, h->st));
+    return EC3D_OK;
+}
+
+template <int MODE>
+static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
+{
+    Solver &s = h->sol;
+    const unsigned expected = (unsigned)(h->nblkAir + h->nblkCond);
+    k_air_spmv<MODE, 32, 8><<<h->airGrid, dim3(32, 8), 0, h->st>>>(h->G, h->cf, h->d_geo, vs, ctl, h->zc, s.partials,
+                                                                  s.pstride, expected, h->nblkCond == 0 ? 1 : 0);
+    g_launches.fetch_add(1);
+    if (h->nblkCond == 0) return 1;
+    k_cond_spmv<MODE><<<h->nblkCond, 256, 0, h->st>>>(h->G, h->cf, h->d_mc, h->d_geo, h->d_mat, h->d_cond_cells,
+                                                      h->ncond, vs, ctl, s.partials, s.pstride, h->nblkAir, expected);
+    g_launches.fetch_add(1);
+    return 2;
+}
+
+static int h_spmv(ec3d_handle *h, int mode, const VecSet &vs, const IterCtl &ctl)
+{
+    switch (mode) {
+    case MODE_AP:   return launch_stencil<MODE_AP>(h, vs, ctl);
+    case MODE_AS:   return launch_stencil<MODE_AS>(h, vs, ctl);
+    case MODE_INIT: return launch_stencil<MODE_INIT>(h, vs, ctl);
+    default:        return launch_stencil<MODE_PLAIN>(h, vs, ctl);
+    }
+}
+
+extern "C" int ec3d_nccl_unique_id(void *id128)
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    if (!id128) return EC3D_ERR_ARG;
+    ncclUniqueId id;
+    NCCL_TRY(ncclGetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_destroy(ec3d_handle *h)
+{
+    if (!h) return EC3D_OK;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    if (h->sol.graph) cudaGraphExecDestroy(h->sol.graph);
+    if (h->comm) ncclCommDestroy(h->comm);
+    cudaFree(h->d_mc); cudaFree(h->d_geo); cudaFree(h->d_mat); cudaFree(h->d_cond_cells); cudaFree(h->d_flags);
+    cudaFree(h->vecs); cudaFree(h->sol.sc); cudaFree(h->sol.iter_base); cudaFree(h->sol.partials);
+    cudaFree(h->d_nod_ptr); cudaFree(h->d_nods); cudaFree(h->d_num_Vmech); cudaFree(h->d_comp);
+    cudaFree(h->d_new_nodes); cudaFree(h->d_ms); cudaFree(h->d_fun_vely); cudaFree(h->d_vmech); cudaFree(h->d_oob);
+    if (h->sol.h_flags) cudaFreeHost(h->sol.h_flags);
+    if (h->h_src) cudaFreeHost(h->h_src);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return EC3D_OK;
+}
+
+static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
+{
+    const int sdx = cfg->sdx, sdy = cfg->sdy, sdz = cfg->sdz;
+    const long long kdz = (long long)sdx * sdy, nC = kdz * sdz;
+    if (sdx < 3 || sdy < 3 || sdz < 3) { ec3d_set_error("grid must be at least 3 cells along each axis"); return EC3D_ERR_ARG; }
+    if (cfg->size_PHYS_C > 1) { ec3d_set_error("more than one conductor domain is not supported (reference quirk B4)"); return EC3D_ERR_UNSUPPORTED; }
+    if (cfg->size_PHYS_C == 1 && (!cfg->cond_nod_ptr || !cfg->cond_nod || !cfg->cond_valdom)) { ec3d_set_error("missing conductor arrays"); return EC3D_ERR_ARG; }
+    if (!cfg->geoPHYS || !cfg->geoPHYS_C || !cfg->valPHYS || cfg->nmat < 1) { ec3d_set_error("missing grid arrays"); return EC3D_ERR_ARG; }
+    if (cfg->numfun > EC3D_MAX_FUN) { ec3d_set_error("too many source functions"); return EC3D_ERR_UNSUPPORTED; }
+    const long long Nc = cfg->size_PHYS_C ? (cfg->cond_nod_ptr[1] - cfg->cond_nod_ptr[0]) : 0;
+    if (3 * nC + Nc >= 2147483647LL) { ec3d_set_error("unknown count exceeds 32-bit indices"); return EC3D_ERR_ARG; }
+    h->nranks = std::max(1, cfg->nranks);
+    h->rank = cfg->nranks > 1 ? cfg->rank : 0;
+    h->size_PHYS_C = cfg->size_PHYS_C;
+    h->nCells0 = Nc; h->nGlob = 3 * nC + Nc;
+    h->dt = cfg->dt; h->tol = cfg->tolerance; h->itmax = cfg->itmax;
+    for (int a = 0; a < 3; ++a) h->delta[a] = cfg->delta[a];
+    h->valdom = cfg->size_PHYS_C ? cfg->cond_valdom[0] : 0.0;
+
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) { ec3d_set_error("no CUDA device"); return EC3D_ERR_CUDA; }
+    if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
+    CUDA_TRY(cudaGetDevice(&h->device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    for (auto &e : h->ev) CUDA_TRY(cudaEventCreate(&e));
+
+    // ---- slab partition ----
+    std::vector<long long> cpp(sdz, 0);          // conductor cells per plane
+    for (long long q = 0; q < Nc; ++q) cpp[(cfg->cond_nod[q] - 1) / kdz]++;
+    std::vector<int> kstart(h->nranks + 1, 0);
+    {
+        std::vector<int64_t> cpp64(cpp.begin(), cpp.end());
+        int rc = ec3d_partition_planes(sdx, sdy, sdz, cpp64.data(), h->nranks, kstart.data());
+        if (rc) return rc;
+    }
+    SlabGeom &G = h->G;
+    memset(&G, 0, sizeof(G));
+    G.sdx = sdx; G.sdy = sdy; G.sdz = sdz; G.kdz = (int)kdz; G.nC = nC;
+    G.k0 = kstart[h->rank]; G.k1 = kstart[h->rank + 1]; G.nzl = G.k1 - G.k0;
+    std::vector<long long> ucum(sdz + 1, 0);      // U numbering is k-major for one domain
+    for (int k = 0; k < sdz; ++k) ucum[k + 1] = ucum[k] + cpp[k];
+    auto clampk = [&](int k) { return std::min(std::max(k, 0), sdz); };
+    const long long u_lo = ucum[clampk(G.k0 - 2)], u_own0 = ucum[G.k0], u_own1 = ucum[G.k1], u_hi = ucum[clampk(G.k1 + 2)];
+    G.nUlo = u_own0 - u_lo; G.nUown = u_own1 - u_own0; G.nUhi = u_hi - u_own1;
+    h->nU_send_lo = ucum[clampk(G.k0 + 2)] - u_own0;
+    h->nU_send_hi = u_own1 - ucum[clampk(G.k1 - 2)];
+    long long segA = (long long)(G.nzl + 2) * kdz;
+    segA += segA & 1;
+    G.segA = segA; G.offU = 3 * segA;
+    // keep the owned U range 16-byte aligned when possible: pad the front if nUlo is odd
+    long long upad = G.nUlo & 1;
+    G.offU += upad;
+    G.ltot = G.offU + G.nUlo + G.nUown + G.nUhi + 2;
+    G.u_first_global = u_lo;
+    G.gbase = (int)(3 * nC + 1 + u_lo);
+    for (int c = 0; c < 3; ++c) {
+        G.own_off[c] = c * segA + kdz; G.own_len[c] = (long long)G.nzl * kdz;
+        G.glob_off[c] = c * nC + (long long)G.k0 * kdz;
+    }
+    G.own_off[3] = G.offU + G.nUlo; G.own_len[3] = G.nUown; G.glob_off[3] = 3 * nC + u_own0;
+    G.own_cum[0] = 0;
+    for (int c = 0; c < 4; ++c) G.own_cum[c + 1] = G.own_cum[c] + G.own_len[c];
+    G.n_own = G.own_cum[4];
+
+    // ---- coefficient tables ----
+    build_coef(cfg->delta, cfg->dt, cfg->BND, h->cf);
+    h->nmat = cfg->nmat;
+    {
+        std::vector<MatCoef> mc(cfg->nmat);
+        for (int m = 0; m < cfg->nmat; ++m) build_matcoef(cfg->delta, cfg->dt, cfg->valPHYS + 5 * m, mc[m]);
+        CUDA_TRY(cudaMalloc(&h->d_mc, mc.size() * sizeof(MatCoef)));
+        CUDA_TRY(cudaMemcpy(h->d_mc, mc.data(), mc.size() * sizeof(MatCoef), cudaMemcpyHostToDevice));
+    }
+    // ---- maps: planes [k0-2, k1+2), zero outside the domain ----
+    {
+        const long long gplanes = G.nzl + 4;
+        CUDA_TRY(cudaMalloc(&h->d_geo, (size_t)(gplanes * kdz) * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_mat, (size_t)(gplanes * kdz)));
+        CUDA_TRY(cudaMemset(h->d_geo, 0, (size_t)(gplanes * kdz) * sizeof(int)));
+        CUDA_TRY(cudaMemset(h->d_mat, 0, (size_t)(gplanes * kdz)));
+        const int ka = std::max(G.k0 - 2, 0), kb = std::min(G.k1 + 2, sdz);
+        CUDA_TRY(cudaMemcpy(h->d_geo + (long long)(ka - (G.k0 - 2)) * kdz, cfg->geoPHYS_C + (long long)ka * kdz,
+                            (size_t)((kb - ka) * kdz) * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d_mat + (long long)(ka - (G.k0 - 2)) * kdz, cfg->geoPHYS + (long long)ka * kdz,
+                            (size_t)((kb - ka) * kdz), cudaMemcpyHostToDevice));
+    }
+    // ---- owned conductor cells (k,j,i order; the list is ascending like PHYS_C%nod) ----
+    {
+        std::vector<int> cells;
+        cells.reserve((size_t)G.nUown);
+        for (long long q = 0; q < Nc; ++q) {
+            const long long c0 = cfg->cond_nod[q] - 1;
+            const int k = (int)(c0 / kdz);
+            if (k >= G.k0 && k < G.k1) cells.push_back((int)c0);
+        }
+        if (!std::is_sorted(cells.begin(), cells.end())) { ec3d_set_error("PHYS_C%%nod must be ascending"); return EC3D_ERR_ARG; }
+        if ((long long)cells.size() != G.nUown) { ec3d_set_error("conductor list inconsistent with planes"); return EC3D_ERR_ARG; }
+        // geoPHYS_C must number the conductor cells consecutively in k,j,i order
+        for (size_t q = 0; q < cells.size(); q += std::max<size_t>(1, cells.size() / 64)) {
+            if (cfg->geoPHYS_C[cells[q]] != (int)(3 * nC + 1 + u_own0 + (long long)q)) { ec3d_set_error("geoPHYS_C numbering is not k,j,i ordered"); return EC3D_ERR_ARG; }
+        }
+        h->ncond = (int)cells.size();
+        if (h->ncond) {
+            CUDA_TRY(cudaMalloc(&h->d_cond_cells, cells.size() * sizeof(int)));
+            CUDA_TRY(cudaMemcpy(h->d_cond_cells, cells.data(), cells.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMalloc(&h->d_flags, cells.size()));
+        }
+    }
+    // ---- vectors ----
+    const int NV = 10;   // Uaf Jaf R R0 P AP S AS tmpx tmpy
+    CUDA_TRY(cudaMalloc(&h->vecs, (size_t)G.ltot * NV * sizeof(double)));
+    CUDA_TRY(cudaMemset(h->vecs, 0, (size_t)G.ltot * NV * sizeof(double)));
+    Solver &s = h->sol;
+    s.G = G; s.st = h->st;
+    h->Uaf = h->vecs; h->Jaf = h->vecs + G.ltot;
+    s.X = h->Uaf;
+    s.R = h->vecs + 2 * G.ltot; s.R0 = h->vecs + 3 * G.ltot; s.P = h->vecs + 4 * G.ltot; s.AP = h->vecs + 5 * G.ltot;
+    s.S = h->vecs + 6 * G.ltot; s.AS = h->vecs + 7 * G.ltot;
+    h->tmpx = h->vecs + 8 * G.ltot; h->tmpy = h->vecs + 9 * G.ltot;
+    CUDA_TRY(cudaMalloc(&s.sc, sizeof(Scal)));
+    CUDA_TRY(cudaMemset(s.sc, 0, sizeof(Scal)));
+    CUDA_TRY(cudaMalloc(&s.iter_base, sizeof(int)));
+    CUDA_TRY(cudaHostAlloc(&s.h_flags, 4 * sizeof(int), cudaHostAllocDefault));
+    bool even = true;
+    for (int c = 0; c < 4; ++c) even = even && (G.own_off[c] % 2 == 0) && (G.own_len[c] % 2 == 0);
+    s.vec = even ? 2 : 1;
+    s.nblkVec = vec_blocks(G.n_own, s.vec);
+    // ---- stencil launch shape ----
+    {
+        const int tx = (sdx + 31) / 32, ty = (sdy + 7) / 8;
+        const int tiles = tx * ty;
+        const int want = (2 * 148 * 8 + tiles - 1) / tiles;             // z chunks for ~2 waves of 8 CTAs/SM
+        int zc = std::max(1, std::min(32, G.nzl / std::max(1, want)));
+        const char *ez = getenv("EC3D_ZC");
+        if (ez && atoi(ez) > 0) zc = atoi(ez);
+        h->zc = zc;
+        h->airGrid = dim3(tx, ty, (G.nzl + zc - 1) / zc);
+        h->nblkAir = tx * ty * (int)h->airGrid.z;
+        h->nblkCond = (h->ncond + 255) / 256;
+    }
+    s.pstride = std::max(h->nblkAir + h->nblkCond, s.nblkVec) + 8;
+    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 2 * sizeof(double)));
+    s.multi = h->nranks > 1;
+    s.spmv = [h](int mode, const VecSet &vs, const IterCtl &ctl) { return h_spmv(h, mode, vs, ctl); };
+    s.halo = [h](double *v) { return h_halo(h, v); };
+    s.allreduce = [h](int slot, int count) { return h_allreduce(h, slot, count); };
+
+    // ---- validate conductor geometry, classify boundary-cell flags ----
+    if (h->ncond) {
+        int *d_nbad = nullptr;
+        CUDA_TRY(cudaMalloc(&d_nbad, sizeof(int)));
+        CUDA_TRY(cudaMemset(d_nbad, 0, sizeof(int)));
+        k_classify_conductor<<<h->nblkCond, 256, 0, h->st>>>(G, h->cf, h->d_geo, h->d_mat, h->nmat, h->d_cond_cells,
+                                                             h->ncond, h->d_flags, d_nbad);
+        LAUNCHED(h->launches);
+        int nbad = 0;
+        CUDA_TRY(cudaMemcpyAsync(&nbad, d_nbad, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        cudaFree(d_nbad);
+        if (nbad) {
+            ec3d_set_error("%d conductor cells with invalid geometry (on a domain face, thinner than 3 cells at a free "
+                           "face, or bad material id): the reference would STOP (EC3D.f90:717-720)", nbad);
+            return EC3D_ERR_GEOMETRY;
+        }
+    }
+    // ---- sources ----
+    h->numfun = cfg->numfun; h->numMech = cfg->numMech;
+    if (cfg->numfun > 0) {
+        if (!cfg->fun_ex || !cfg->fun_nod_ptr || !cfg->fun_nods || !cfg->fun_num_Vmech || !cfg->fun_move || !cfg->fun_vel_Vmech) {
+            ec3d_set_error("missing source arrays"); return EC3D_ERR_ARG;
+        }
+        const int nf = cfg->numfun;
+        h->h_nod_ptr.assign(cfg->fun_nod_ptr, cfg->fun_nod_ptr + nf + 1);
+        h->h_comp.resize(nf);
+        MotionState ms;
+        memset(&ms, 0, sizeof(ms));
+        ms.movestop[0] = ms.movestop[1] = ms.movestop[2] = 1;               // EC3D.f90:238
+        for (int f = 0; f < nf; ++f) {
+            const char ex = cfg->fun_ex[f];
+            if (ex != 'X' && ex != 'Y' && ex != 'Z') {                        // STOP at EC3D.f90:227/337/363
+                ec3d_set_error("source %d has direction '%c': the reference STOPs (only X/Y/Z)", f, ex);
+                return EC3D_ERR_UNSUPPORTED;
+            }
+            h->h_comp[f] = ex == 'X' ? 0 : ex == 'Y' ? 1 : 2;
+            for (int a = 0; a < 3; ++a) {                                      // EC3D.f90:165-185
+                const int nv = cfg->fun_num_Vmech[3 * f + a], mv = cfg->fun_move[3 * f + a];
+                if (nv == 0 && mv != 0) { ms.shift[f][a] = cfg->fun_vel_Vmech[3 * f + a] * cfg->dt / cfg->delta[a]; h->flag_move = 1; }
+                else if (mv != 0) h->flag_move = 1;
+                if (nv < 0 || nv > cfg->numMech) { ec3d_set_error("num_Vmech out of range"); return EC3D_ERR_ARG; }
+            }
+        }
+        if (h->flag_move && (sdx < 5 || sdy < 5 || sdz < 5)) { ec3d_set_error("moving sources need >= 5 cells per axis"); return EC3D_ERR_UNSUPPORTED; }
+        h->total_nodes = h->h_nod_ptr[nf];
+        CUDA_TRY(cudaMalloc(&h->d_nod_ptr, (nf + 1) * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_nods, std::max(1, h->total_nodes) * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_new_nodes, std::max(1, h->total_nodes) * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_num_Vmech, 3 * nf * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_comp, nf * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_ms, sizeof(MotionState)));
+        CUDA_TRY(cudaMalloc(&h->d_fun_vely, nf * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->d_vmech, std::max(1, cfg->numMech) * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->d_oob, sizeof(int)));
+        CUDA_TRY(cudaMemset(h->d_oob, 0, sizeof(int)));
+        CUDA_TRY(cudaMemset(h->d_new_nodes, 0, std::max(1, h->total_nodes) * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(h->d_nod_ptr, cfg->fun_nod_ptr, (nf + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        if (h->total_nodes) CUDA_TRY(cudaMemcpy(h->d_nods, cfg->fun_nods, h->total_nodes * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d_num_Vmech, cfg->fun_num_Vmech, 3 * nf * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d_comp, h->h_comp.data(), nf * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d_ms, &ms, sizeof(ms), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaHostAlloc(&h->h_src, (nf + std::max(1, cfg->numMech)) * sizeof(double), cudaHostAllocDefault));
+    }
+    // ---- NCCL ----
+    if (h->nranks > 1) {
+        if (!cfg->nccl_id) { ec3d_set_error("nccl_id required for nranks > 1"); return EC3D_ERR_ARG; }
+        if (G.nzl < 2) { ec3d_set_error("each slab needs at least 2 planes"); return EC3D_ERR_ARG; }
+        ncclUniqueId id;
+        memcpy(&id, cfg->nccl_id, 128);
+        NCCL_TRY(ncclCommInitRank(&h->comm, h->nranks, id, h->rank));
+    }
+    // ---- iteration graph (single rank) ----
+    {
+        const char *ge = getenv("EC3D_GRAPH");
+        if (h->nranks == 1 && (!ge || atoi(ge) != 0)) { int rc = solver_build_graph(s, 8); if (rc) return rc; }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_create(const ec3d_config *cfg, ec3d_handle **out)
+{
+    if (!cfg || !out) { ec3d_set_error("null argument"); return EC3D_ERR_ARG; }
+    *out = nullptr;
+    ec3d_handle *h = new ec3d_handle();
+    int rc = create_impl(cfg, h);
+    if (rc != EC3D_OK) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        ec3d_destroy(h);
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    *out = h;
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_sizes(const ec3d_handle *h, int64_t *nCells, int64_t *nCells0, int64_t *nCellsGlob, int32_t *k0,
+                          int32_t *k1, int64_t *n_owned)
+{
+    if (!h) return EC3D_ERR_ARG;
+    if (nCells) *nCells = h->G.nC;
+    if (nCells0) *nCells0 = h->nCells0;
+    if (nCellsGlob) *nCellsGlob = h->nGlob;
+    if (k0) *k0 = h->G.k0;
+    if (k1) *k1 = h->G.k1;
+    if (n_owned) *n_owned = h->G.n_own;
+    return EC3D_OK;
+}
+
+// copies between the reference layout (full-length host vectors) and the local layout
+static int copy_in(ec3d_handle *h, double *dst_local, const double *src_global)
+{
+    const SlabGeom &G = h->G;
+    for (int c = 0; c < 4; ++c)
+        if (G.own_len[c])
+            CUDA_TRY(cudaMemcpyAsync(dst_local + G.own_off[c], src_global + G.glob_off[c], (size_t)G.own_len[c] * sizeof(double),
+                                     cudaMemcpyHostToDevice, h->st));
+    return h_halo(h, dst_local);
+}
+static int copy_out(ec3d_handle *h, double *dst_global, const double *src_local)
+{
+    const SlabGeom &G = h->G;
+    for (int c = 0; c < 4; ++c)
+        if (G.own_len[c])
+            CUDA_TRY(cudaMemcpyAsync(dst_global + G.glob_off[c], src_local + G.own_off[c], (size_t)G.own_len[c] * sizeof(double),
+                                     cudaMemcpyDeviceToHost, h->st));
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_get_fields(ec3d_handle *h, double *Uaf, double *Jaf)
+{
+    if (!h) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if (Uaf && (rc = copy_out(h, Uaf, h->Uaf))) return rc;
+    if (Jaf && (rc = copy_out(h, Jaf, h->Jaf))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_set_fields(ec3d_handle *h, const double *Uaf, const double *Jaf)
+{
+    if (!h) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if (Uaf && (rc = copy_in(h, h->Uaf, Uaf))) return rc;
+    if (Jaf && (rc = copy_in(h, h->Jaf, Jaf))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_get_source_cells(ec3d_handle *h, int32_t *cells)
+{
+    if (!h || !cells) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->total_nodes)
+        CUDA_TRY(cudaMemcpyAsync(cells, h->d_new_nodes, h->total_nodes * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_apply_operator(ec3d_handle *h, const double *x, double *y)
+{
+    if (!h || !x || !y) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = copy_in(h, h->tmpx, x);
+    if (rc) return rc;
+    VecSet vs{h->tmpx, h->tmpy, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const IterCtl ctl{h->sol.sc, h->sol.iter_base, 0};
+    h->launches += h_spmv(h, MODE_PLAIN, vs, ctl);
+    if ((rc = copy_out(h, y, h->tmpy))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    CUDA_TRY(cudaGetLastError());
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_solve_host(ec3d_handle *h, const double *b, double *x, int32_t *iter)
+{
+    if (!h || !b || !x || !iter) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = copy_in(h, h->tmpx, b);
+    if (rc) return rc;
+    Solver &s = h->sol;
+    double *saveX = s.X;
+    s.X = h->tmpy;
+    // the iteration graph was captured with s.X = Uaf; run without it here
+    cudaGraphExec_t g = s.graph; s.graph = nullptr;
+    rc = copy_in(h, h->tmpy, x);
+    if (!rc) rc = solver_run(s, h->tmpx, h->tol, h->itmax, iter);
+    s.graph = g; s.X = saveX;
+    if (rc) return rc;
+    if ((rc = copy_out(h, x, h->tmpy))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return EC3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// timestep body, EC3D.f90:275-433
+// ------------------------------------------------------------------------------------------
+static int stage_scatter(ec3d_handle *h, const double *fun_vely, const double *vmech_vely)
+{
+    const SlabGeom &G = h->G;
+    if (h->numfun == 0) {
+        if (h->flag_move) { /* unreachable: flag_move needs a function */ }
+        return EC3D_OK;
+    }
+    if (!fun_vely || (h->numMech > 0 && !vmech_vely)) { ec3d_set_error("missing source scalars"); return EC3D_ERR_ARG; }
+    // per-step host inputs: numfun + numMech doubles through pinned memory
+    memcpy(h->h_src, fun_vely, h->numfun * sizeof(double));
+    if (h->numMech) memcpy(h->h_src + h->numfun, vmech_vely, h->numMech * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(h->d_fun_vely, h->h_src, h->numfun * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    if (h->numMech)
+        CUDA_TRY(cudaMemcpyAsync(h->d_vmech, h->h_src + h->numfun, h->numMech * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    const SourceDesc sd{h->d_nod_ptr, h->d_nods, h->d_num_Vmech, h->d_comp, h->numfun};
+    if (h->flag_move) {
+        const long long cnt = (long long)G.nzl * G.kdz + G.nUown;
+        const int nb = (int)std::min<long long>((cnt + 255) / 256, 148 * 16);
+        k_clear_nonconductor<<<nb, 256, 0, h->st>>>(G, h->d_geo, h->Jaf, h->size_PHYS_C != 0 ? 1 : 0);
+        LAUNCHED(h->launches);
+        k_motion<<<1, 32, 0, h->st>>>(G, sd, h->d_ms, h->d_vmech, h->dt, h->delta[0], h->delta[1], h->delta[2]);
+        LAUNCHED(h->launches);
+    }
+    for (int f = 0; f < h->numfun; ++f) {
+        const int cnt = h->h_nod_ptr[f + 1] - h->h_nod_ptr[f];
+        if (cnt <= 0) continue;
+        k_scatter<<<(cnt + 255) / 256, 256, 0, h->st>>>(G, sd, h->d_ms, f, h->flag_move, h->d_fun_vely, h->Jaf,
+                                                        h->d_new_nodes, h->d_oob);
+        LAUNCHED(h->launches);
+    }
+    return EC3D_OK;
+}
+
+static int stage_rhs_pre(ec3d_handle *h)
+{
+    if (h->size_PHYS_C == 0) return EC3D_OK;
+    int rc = h_halo(h, h->Uaf);      // the U-row right-hand side reads Az(k+-1) of Uaf
+    if (rc) return rc;
+    if (h->ncond) {
+        k_rhs_pre<<<h->nblkCond, 256, 0, h->st>>>(h->G, h->cf, h->d_geo, h->d_cond_cells, h->ncond, h->d_flags, h->valdom,
+                                                  h->Uaf, h->Jaf);
+        LAUNCHED(h->launches);
+    }
+    return EC3D_OK;
+}
+
+static int stage_solve(ec3d_handle *h, int32_t *iter)
+{
+    CUDA_TRY(cudaEventRecord(h->ev[2], h->st));
+    int it = 0;
+    int rc = solver_run(h->sol, h->Jaf, h->tol, h->itmax, &it);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev[3], h->st));
+    if (iter) *iter = it;
+    return EC3D_OK;
+}
+
+static int stage_rhs_post(ec3d_handle *h)
+{
+    if (h->size_PHYS_C == 0 || h->ncond == 0) return EC3D_OK;
+    k_rhs_post<<<h->nblkCond, 256, 0, h->st>>>(h->G, h->d_cond_cells, h->ncond, h->d_flags, h->valdom, h->Uaf, h->Jaf);
+    LAUNCHED(h->launches);
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_step_stage(ec3d_handle *h, int32_t what, const double *fun_vely, const double *vmech_vely,
+                               int32_t *iter)
+{
+    if (!h) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = EC3D_OK;
+    switch (what) {
+    case 0: rc = stage_scatter(h, fun_vely, vmech_vely); break;
+    case 1: rc = stage_rhs_pre(h); break;
+    case 2: rc = stage_solve(h, iter); break;
+    case 3: rc = stage_rhs_post(h); break;
+    default: ec3d_set_error("bad stage"); return EC3D_ERR_ARG;
+    }
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    CUDA_TRY(cudaGetLastError());
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_step(ec3d_handle *h, const double *fun_vely, const double *vmech_vely, int32_t *iter)
+{
+    if (!h) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
+    int rc;
+    if ((rc = stage_scatter(h, fun_vely, vmech_vely))) return rc;
+    if ((rc = stage_rhs_pre(h))) return rc;
+    if ((rc = stage_solve(h, iter))) return rc;
+    if ((rc = stage_rhs_post(h))) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->last_step_ms = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->last_solve_ms = ms;
+    if (h->d_oob) {
+        int oob = 0;
+        CUDA_TRY(cudaMemcpy(&oob, h->d_oob, sizeof(int), cudaMemcpyDeviceToHost));
+        if (oob) { ec3d_set_error("a moved source cell fell outside the grid"); return EC3D_ERR_GEOMETRY; }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_counters(const ec3d_handle *h, int64_t *launches, int64_t *iterations, double *last_step_ms,
+                             double *last_solve_ms)
+{
+    if (!h) return EC3D_ERR_ARG;
+    if (launches) *launches = h->launches + h->sol.launches;
+    if (iterations) *iterations = h->sol.iterations;
+    if (last_step_ms) *last_step_ms = h->last_step_ms;
+    if (last_solve_ms) *last_solve_ms = h->last_solve_ms;
+    return EC3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// GPU assembly of the reference's CSR, EC3D.f90:465-1049
+// ------------------------------------------------------------------------------------------
+static int scan_i32_to_i64(cudaStream_t st, const int *in, long long *out, long long n, long long *total_host, long long &launches)
+{
+    const int per = SCAN_T * SCAN_I;
+    const int nb = (int)((n + per - 1) / per);
+    long long *bsum = nullptr, *dtotal = nullptr;
+    CUDA_TRY(cudaMalloc(&bsum, (size_t)std::max(nb, 1) * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&dtotal, sizeof(long long)));
+    k_scan_block<<<nb, SCAN_T, 0, st>>>(in, out, n, bsum);
+    k_scan_top<<<1, 1, 0, st>>>(bsum, nb, dtotal);
+    k_scan_add<<<nb, SCAN_T, 0, st>>>(out, n, bsum);
+    launches += 3; g_launches.fetch_add(3);
+    CUDA_TRY(cudaMemcpyAsync(total_host, dtotal, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(bsum); cudaFree(dtotal);
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_assemble_csr(ec3d_handle *h, int64_t num_nz[5], int32_t num_bnd[6], int32_t *irow, int32_t *jcol,
+                                 double *valA, int32_t *cel_bndX, int32_t *cel_bndY, int32_t *cel_bndZ,
+                                 int32_t *cel_bndUx, int32_t *cel_bndUy, int32_t *cel_bndUz)
+{
+    if (!h || !num_nz || !num_bnd) return EC3D_ERR_ARG;
+    if (h->nranks != 1) { ec3d_set_error("ec3d_assemble_csr needs a single-rank handle"); return EC3D_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const SlabGeom &G = h->G;
+    const long long n = h->nGlob, nC = G.nC;
+    int *d_len = nullptr; long long *d_off = nullptr;
+    CUDA_TRY(cudaMalloc(&d_len, (size_t)n * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_off, (size_t)(n + 1) * sizeof(long long)));
+    const int nbc = (int)((nC + 255) / 256);
+    k_asm_count<<<nbc, 256, 0, h->st>>>(G, h->cf, h->d_geo, d_len);
+    LAUNCHED(h->launches);
+    long long total = 0;
+    int rc = scan_i32_to_i64(h->st, d_len, d_off, n, &total, h->launches);
+    if (rc) { cudaFree(d_len); cudaFree(d_off); return rc; }
+    // block counts from the offsets at the block starts
+    long long offs[3];
+    for (int c = 1; c <= 3; ++c) CUDA_TRY(cudaMemcpy(&offs[c - 1], d_off + c * nC, sizeof(long long), cudaMemcpyDeviceToHost));
+    num_nz[0] = offs[0]; num_nz[1] = offs[1] - offs[0]; num_nz[2] = offs[2] - offs[1]; num_nz[3] = total - offs[2];
+    num_nz[4] = total;
+    // boundary-cell lists: compaction of the per-conductor-cell flags, k,j,i order
+    int32_t *lists[6] = {cel_bndX, cel_bndY, cel_bndZ, cel_bndUx, cel_bndUy, cel_bndUz};
+    int *d_bit = nullptr, *d_list = nullptr; long long *d_pos = nullptr;
+    const int nc = h->ncond;
+    if (nc) {
+        CUDA_TRY(cudaMalloc(&d_bit, (size_t)nc * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&d_pos, (size_t)nc * sizeof(long long)));
+        CUDA_TRY(cudaMalloc(&d_list, (size_t)nc * sizeof(int)));
+    }
+    for (int b = 0; b < 6; ++b) {
+        num_bnd[b] = 0;
+        if (!nc) continue;
+        k_flag_bit<<<(nc + 255) / 256, 256, 0, h->st>>>(h->d_flags, nc, b, d_bit);
+        LAUNCHED(h->launches);
+        long long cnt = 0;
+        if ((rc = scan_i32_to_i64(h->st, d_bit, d_pos, nc, &cnt, h->launches))) break;
+        num_bnd[b] = (int32_t)cnt;
+        if (lists[b] && cnt) {
+            k_compact_list<<<(nc + 255) / 256, 256, 0, h->st>>>(G, h->d_flags, nc, b, d_pos, h->d_cond_cells, h->d_geo, d_list);
+            LAUNCHED(h->launches);
+            CUDA_TRY(cudaMemcpyAsync(lists[b], d_list, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+            CUDA_TRY(cudaStreamSynchronize(h->st));
+        }
+    }
+    cudaFree(d_bit); cudaFree(d_pos); cudaFree(d_list);
+    if (rc) { cudaFree(d_len); cudaFree(d_off); return rc; }
+    if (total + 1 > 2147483647LL) {
+        cudaFree(d_len); cudaFree(d_off);
+        ec3d_set_error("nnz = %lld does not fit the reference's default INTEGER", total);
+        return EC3D_ERR_NNZ_OVERFLOW;
+    }
+    if (irow) {
+        int *d_irow = nullptr;
+        CUDA_TRY(cudaMalloc(&d_irow, (size_t)(n + 1) * sizeof(int)));
+        k_off_to_irow<<<(int)((n + 1 + 255) / 256), 256, 0, h->st>>>(d_off, n, total, d_irow);
+        LAUNCHED(h->launches);
+        CUDA_TRY(cudaMemcpyAsync(irow, d_irow, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        cudaFree(d_irow);
+    }
+    if (jcol && valA) {
+        int *d_jcol = nullptr; double *d_val = nullptr;
+        CUDA_TRY(cudaMalloc(&d_jcol, (size_t)total * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&d_val, (size_t)total * sizeof(double)));
+        k_asm_fill<<<nbc, 256, 0, h->st>>>(G, h->cf, h->d_mc, h->d_geo, h->d_mat, d_off, d_jcol, d_val);
+        LAUNCHED(h->launches);
+        CUDA_TRY(cudaMemcpyAsync(jcol, d_jcol, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CUDA_TRY(cudaMemcpyAsync(valA, d_val, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        cudaFree(d_jcol); cudaFree(d_val);
+    }
+    cudaFree(d_len); cudaFree(d_off);
+    CUDA_TRY(cudaGetLastError());
+    return EC3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// measurement hooks
+// ------------------------------------------------------------------------------------------
+__global__ void k_bench_scalars(Scal *sc, int *iter_base)
+{
+    // values that keep every guard open and the updates finite while timing single kernels
+    sc->done = 0; sc->tol = 0.0; sc->itmax = 1 << 30; sc->counter = 0u;
+    sc->red[RED_BB] = 1.0; sc->red[RED_RR_INIT] = 1.0; sc->red[RED_APR0] = 1.0e30; sc->red[RED_SS] = 1.0;
+    sc->red[RED_ASS] = 1.0e-30; sc->red[RED_ASAS] = 1.0; sc->red[RED_RR] = 1.0; sc->red[RED_RR0N] = 1.0e-30;
+    sc->rr0[0] = sc->rr0[1] = 1.0; sc->alpha = 1e-30; sc->omega = 1.0;
+    *iter_base = 4;
+}
+
+extern "C" int ec3d_bench_kernel(ec3d_handle *h, int32_t which, int32_t warm, int32_t reps, double *ms)
+{
+    if (!h || !ms || reps < 1) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    Solver &s = h->sol;
+    const SlabGeom &G = h->G;
+    const unsigned nb = (unsigned)s.nblkVec;
+    const IterCtl ctl{s.sc, s.iter_base, 1};
+    auto one = [&]() -> int {
+        switch (which) {
+        case 0: { VecSet vs{s.P, s.AP, s.R0, nullptr, nullptr, nullptr, nullptr}; h->launches += h_spmv(h, MODE_AP, vs, ctl); break; }
+        case 1: { VecSet vs{s.S, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr}; h->launches += h_spmv(h, MODE_AS, vs, ctl); break; }
+        case 2:
+            if (s.vec == 2) k_s_update<2><<<nb, 256, 0, h->st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
+            else k_s_update<1><<<nb, 256, 0, h->st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
+            LAUNCHED(h->launches); break;
+        case 3:
+            if (s.vec == 2) k_xr_update<2><<<nb, 256, 0, h->st>>>(G, h->tmpx, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
+            else k_xr_update<1><<<nb, 256, 0, h->st>>>(G, h->tmpx, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
+            LAUNCHED(h->launches); break;
+        case 4:
+            if (s.vec == 2) k_p_update<2><<<nb, 256, 0, h->st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
+            else k_p_update<1><<<nb, 256, 0, h->st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
+            LAUNCHED(h->launches); break;
+        default: return EC3D_ERR_ARG;
+        }
+        return EC3D_OK;
+    };
+    k_bench_scalars<<<1, 1, 0, h->st>>>(s.sc, s.iter_base);
+    // deterministic non-trivial data: fill the Krylov vectors from a splitmix-like pattern
+    k_fill<<<148 * 4, 256, 0, h->st>>>(s.R, G.ltot * 6, 0.5);
+    for (int q = 0; q < warm; ++q) { int rc = one(); if (rc) return rc; k_bench_scalars<<<1, 1, 0, h->st>>>(s.sc, s.iter_base); }
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    float total = 0.f;
+    for (int q = 0; q < reps; ++q) {
+        k_bench_scalars<<<1, 1, 0, h->st>>>(s.sc, s.iter_base);
+        CUDA_TRY(cudaEventRecord(h->ev[0], h->st));
+        int rc = one(); if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev[1], h->st));
+        CUDA_TRY(cudaStreamSynchronize(h->st));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+        total += t;
+    }
+    *ms = total / reps;
+    CUDA_TRY(cudaGetLastError());
+    return EC3D_OK;
+}

@@ -1,0 +1,493 @@
+// ec3d_kernels.cuh -- sm_100a kernels of the EC3D hot path: matrix-free SpMV (air + conductor
+// parts), CSR SpMV (drop-in mode), fused BiCGSTABwr vector kernels, deterministic reductions.
+//
+// Arithmetic: fp64 with explicit round-to-nearest mul/add (__dmul_rn/__dadd_rn are never
+// contracted into FMA), each row summed in ascending column order starting from 0 -- the order of
+// the reference's sprsAx (solvers.f90:54-61) -- so the matrix-free operator is bit-identical to a
+// sequential CSR row sum.  Dot products use a fixed reduction tree (thread-sequential, warp
+// butterfly, warp-0 across warps, last block over the per-block partials in index order), hence
+// results are reproducible run to run; they differ from the reference's sequential dot_product
+// only by summation order.
+#pragma once
+#include "ec3d_common.cuh"
+#include "ec3d_rows.cuh"
+
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DADD(a, b) __dadd_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+
+enum { MODE_PLAIN = 0, MODE_AP = 1, MODE_AS = 2, MODE_INIT = 3 };
+
+struct VecSet {
+    const double *x;   // SpMV input
+    double *y;         // SpMV output (AP / AS / plain)
+    const double *r0;  // MODE_AP
+    const double *b;   // MODE_INIT
+    double *R, *R0, *P;// MODE_INIT outputs
+};
+
+// --------------------------------------------------------------------------------------------
+// reductions
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = DADD(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Sum over the block; result valid in thread 0.  blockDim.x*blockDim.y*blockDim.z <= 1024.
+__device__ __forceinline__ double block_sum(double v, double *sh /* >= 32 doubles */)
+{
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthr = blockDim.x * blockDim.y * blockDim.z;
+    const int lane = tid & 31, w = tid >> 5, nw = (nthr + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (tid == 0) {
+        for (int q = 0; q < nw; ++q) r = DADD(r, sh[q]);
+    }
+    return r;
+}
+
+// Stores this block's partial(s); the last block of the GROUP of kernels that share `sc->counter`
+// (expected = total number of blocks that will call this with the same partials array) sums all
+// partials in index order and writes sc->red[slot0], sc->red[slot1].
+template <int NRED>
+__device__ __forceinline__ void reduce_epilogue(double a0, double a1, double *partials, int pstride, int pidx,
+                                                unsigned expected, Scal *sc, int slot0, int slot1, double *sh)
+{
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthr = blockDim.x * blockDim.y * blockDim.z;
+    double s0 = block_sum(a0, sh);
+    double s1 = 0.0;
+    if (NRED > 1) s1 = block_sum(a1, sh);
+    __shared__ unsigned ticket_s;
+    if (tid == 0) {
+        partials[pidx] = s0;
+        if (NRED > 1) partials[pstride + pidx] = s1;
+        __threadfence();
+        ticket_s = atomicAdd(&sc->counter, 1u);
+    }
+    __syncthreads();
+    if (ticket_s != expected - 1) return;
+    __threadfence();
+    double t0 = 0.0, t1 = 0.0;
+    for (unsigned q = tid; q < expected; q += nthr) {
+        t0 = DADD(t0, __ldcg(partials + q));
+        if (NRED > 1) t1 = DADD(t1, __ldcg(partials + pstride + q));
+    }
+    t0 = block_sum(t0, sh);
+    if (NRED > 1) t1 = block_sum(t1, sh);
+    if (tid == 0) {
+        sc->red[slot0] = t0;
+        if (NRED > 1) sc->red[slot1] = t1;
+        sc->counter = 0u;
+        __threadfence();
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// solver control: every kernel of iteration `it` decides from device scalars whether to run.
+// --------------------------------------------------------------------------------------------
+struct IterCtl {
+    Scal *sc;
+    const int *iter_base;  // device counter: iterations completed by previous launches
+    int it_off;            // this kernel belongs to iteration *iter_base + it_off (1-based)
+};
+
+__device__ __forceinline__ bool is_block0()
+{
+    return (blockIdx.x | blockIdx.y | blockIdx.z) == 0 &&
+           (threadIdx.x | threadIdx.y | threadIdx.z) == 0;
+}
+
+// guard of the first kernel of an iteration (SpMV A*p).  solvers.f90:23-29.
+__device__ __forceinline__ bool guard_ap(const IterCtl &c, int &it)
+{
+    Scal *sc = c.sc;
+    if (sc->done) return false;
+    it = *c.iter_base + c.it_off;
+    if (it == 1 && sc->red[RED_BB] == 0.0) {            // Bnorm == 0 -> RETURN with iter = 0
+        if (is_block0()) { sc->exit_kind = 4; sc->final_iter = 0; sc->done = 1; }
+        return false;
+    }
+    if (it - 1 > sc->itmax) {                           // IF (iter > itmax) ... EXIT
+        if (is_block0()) { sc->exit_kind = 3; sc->final_iter = it - 1; sc->done = 1; }
+        return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ bool s_converged(const Scal *sc)
+{
+    return sqrt(sc->red[RED_SS]) / sqrt(sc->red[RED_BB]) < sc->tol;   // solvers.f90:34
+}
+
+// --------------------------------------------------------------------------------------------
+// SpMV row epilogue
+// --------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void row_epilogue(double y, long long idx, double xc, const VecSet &vs, double &a0,
+                                             double &a1)
+{
+    if (MODE == MODE_PLAIN) {
+        vs.y[idx] = y;
+    } else if (MODE == MODE_AP) {
+        vs.y[idx] = y;
+        a0 = DADD(a0, DMUL(y, __ldg(vs.r0 + idx)));              // (AP,R0)   solvers.f90:32
+    } else if (MODE == MODE_AS) {
+        vs.y[idx] = y;
+        a0 = DADD(a0, DMUL(y, xc));                              // (AS,S)    solvers.f90:40
+        a1 = DADD(a1, DMUL(y, y));                               // (AS,AS)
+    } else {
+        const double bb = __ldg(vs.b + idx);
+        const double r = DSUB(bb, y);                            // R = B - A*X  solvers.f90:14-19
+        vs.R[idx] = r; vs.R0[idx] = r; vs.P[idx] = r;
+        a0 = DADD(a0, DMUL(bb, bb));                             // ||b||^2
+        a1 = DADD(a1, DMUL(r, r));                               // (R,R0) with R0 = R
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ bool spmv_guard(const IterCtl &c)
+{
+    if (MODE == MODE_AP) { int it; return guard_ap(c, it); }
+    if (MODE == MODE_AS) {
+        if (c.sc->done) return false;
+        if (s_converged(c.sc)) return false;
+    }
+    return true;
+}
+
+// --------------------------------------------------------------------------------------------
+// K2a: matrix-free SpMV, non-conductor cells (7-point Laplacian with the reference's boundary
+// rows, EC3D.f90:528-654).  One thread per (i,j) column of a TX x TY tile marching over `zc`
+// planes with the k-1/k/k+1 values of the three components in registers; x/y neighbours come
+// through L1.  Conductor cells are skipped here and handled by k_cond_spmv.
+// --------------------------------------------------------------------------------------------
+template <int MODE, int TX, int TY>
+__global__ void __launch_bounds__(TX *TY)
+k_air_spmv(const SlabGeom G, const Coef cf, const int *__restrict__ geo, const VecSet vs, const IterCtl ctl,
+           const int zc, double *partials, const int pstride, const unsigned expected, const int finalize_here)
+{
+    __shared__ double sh[32];
+    if (!spmv_guard<MODE>(ctl)) return;
+    const int i = blockIdx.x * TX + threadIdx.x, j = blockIdx.y * TY + threadIdx.y;
+    const int kb = G.k0 + blockIdx.z * zc;
+    const int ke = min(kb + zc, G.k1);
+    double a0 = 0.0, a1 = 0.0;
+    if (i < G.sdx && j < G.sdy) {
+        const int sdx = G.sdx, kdz = G.kdz;
+        const long long col = (long long)j * sdx + i;
+        const bool xl = (i == 0), xh = (i == sdx - 1), yl = (j == 0), yh = (j == G.sdy - 1);
+        const double cxm = xh ? cf.bhi[0] : cf.msx, cxp = xl ? cf.blo[0] : cf.msx;
+        const double cym = yh ? cf.bhi[1] : cf.msy, cyp = yl ? cf.blo[1] : cf.msy;
+        const int bxy = (int)(xl | xh) | ((int)(yl | yh) << 1);
+        const double *__restrict__ x0 = vs.x;
+        const double *__restrict__ x1 = vs.x + G.segA;
+        const double *__restrict__ x2 = vs.x + 2 * G.segA;
+        long long p = (long long)(kb - G.k0 + 1) * kdz + col;     // local offset of (i,j,kb)
+        const int *gp = geo + (long long)(kb - G.k0 + 2) * kdz + col;
+        double c0 = x0[p], c1 = x1[p], c2 = x2[p];
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+        if (kb > 0) { m0 = x0[p - kdz]; m1 = x1[p - kdz]; m2 = x2[p - kdz]; }
+        for (int k = kb; k < ke; ++k, p += kdz, gp += kdz) {
+            const bool zl = (k == 0), zh = (k == G.sdz - 1);
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+            if (!zh) { p0 = x0[p + kdz]; p1 = x1[p + kdz]; p2 = x2[p + kdz]; }
+            const int g = __ldg(gp);
+            if (g == 0) {
+                const double czm = zh ? cf.bhi[2] : cf.msz, czp = zl ? cf.blo[2] : cf.msz;
+                const int bm = bxy | ((int)(zl | zh) << 2);
+                const double dg = bm ? cf.diag_b[bm] : cf.diag_int;
+#define AIR_ROW(XC, CM, CC, CP, COMP)                                                   \
+                {                                                                       \
+                    double s = 0.0;                                                     \
+                    if (!zl) s = DADD(s, DMUL(czm, CM));                                \
+                    if (!yl) s = DADD(s, DMUL(cym, XC[p - sdx]));                       \
+                    if (!xl) s = DADD(s, DMUL(cxm, XC[p - 1]));                         \
+                    s = DADD(s, DMUL(dg, CC));                                          \
+                    if (!xh) s = DADD(s, DMUL(cxp, XC[p + 1]));                         \
+                    if (!yh) s = DADD(s, DMUL(cyp, XC[p + sdx]));                       \
+                    if (!zh) s = DADD(s, DMUL(czp, CP));                                \
+                    row_epilogue<MODE>(s, (long long)(COMP) * G.segA + p, CC, vs, a0, a1); \
+                }
+                AIR_ROW(x0, m0, c0, p0, 0)
+                AIR_ROW(x1, m1, c1, p1, 1)
+                AIR_ROW(x2, m2, c2, p2, 2)
+#undef AIR_ROW
+            }
+            m0 = c0; m1 = c1; m2 = c2;
+            c0 = p0; c1 = p1; c2 = p2;
+        }
+    }
+    if (MODE != MODE_PLAIN) {
+        const int pidx = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        // INIT reduces (bb, rr), AS reduces (ass, asas), AP reduces (apr0)
+        if (MODE == MODE_AP)
+            reduce_epilogue<1>(a0, 0.0, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
+                               RED_APR0, RED_APR0, sh);
+        else if (MODE == MODE_AS)
+            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
+                               RED_ASS, RED_ASAS, sh);
+        else
+            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
+                               RED_BB, RED_RR_INIT, sh);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// K2b: matrix-free SpMV, conductor cells: three A rows with convection, 2C/dt and grad-U coupling
+// (EC3D.f90:656-710) plus the U row (EC3D.f90:766-922).  One thread per owned conductor cell.
+// --------------------------------------------------------------------------------------------
+struct GatherVisitor {
+    const double *__restrict__ x;
+    long long segA, offU, cell_shift;   // local A index = comp*segA + cell0 - cell_shift
+    int gbase;
+    double s;
+    __device__ __forceinline__ void a(int comp, long long cell0, double coef)
+    {
+        s = DADD(s, DMUL(coef, x[comp * segA + (cell0 - cell_shift)]));
+    }
+    __device__ __forceinline__ void u(int g, double coef) { s = DADD(s, DMUL(coef, x[offU + (g - gbase)])); }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_cond_spmv(const SlabGeom G, const Coef cf, const MatCoef *__restrict__ mcs, const int *__restrict__ geo,
+            const signed char *__restrict__ mat, const int *__restrict__ cond_cells, const int ncond,
+            const VecSet vs, const IterCtl ctl, double *partials, const int pstride, const int pbase,
+            const unsigned expected)
+{
+    __shared__ double sh[32];
+    if (!spmv_guard<MODE>(ctl)) return;
+    double a0 = 0.0, a1 = 0.0;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ncond) {
+        const int cell0 = cond_cells[t];
+        const int k = cell0 / G.kdz, rem = cell0 - k * G.kdz, j = rem / G.sdx, i = rem - j * G.sdx;
+        GeoView gv{geo, G.sdx, G.sdy, G.kdz, G.k0 - 2, G.nzl + 4};
+        const long long cell_shift = (long long)(G.k0 - 1) * G.kdz;
+        const long long lp = (long long)cell0 - cell_shift;
+        const long long lmat = (long long)cell0 - (long long)(G.k0 - 2) * G.kdz;
+        const MatCoef mc = mcs[mat[lmat] - 1];
+        GatherVisitor v{vs.x, G.segA, G.offU, cell_shift, G.gbase, 0.0};
+#pragma unroll
+        for (int comp = 0; comp < 3; ++comp) {
+            v.s = 0.0;
+            cond_a_row(mc, gv, i, j, k, comp, v);
+            row_epilogue<MODE>(v.s, comp * G.segA + lp, vs.x[comp * G.segA + lp], vs, a0, a1);
+        }
+        v.s = 0.0;
+        cond_u_row(cf, gv, i, j, k, 3, v);
+        const long long lu = G.offU + (gv.at(i, j, k) - G.gbase);
+        row_epilogue<MODE>(v.s, lu, vs.x[lu], vs, a0, a1);
+    }
+    if (MODE != MODE_PLAIN) {
+        const int pidx = pbase + blockIdx.x;
+        if (MODE == MODE_AP)
+            reduce_epilogue<1>(a0, 0.0, partials, pstride, pidx, expected, ctl.sc, RED_APR0, RED_APR0, sh);
+        else if (MODE == MODE_AS)
+            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, sh);
+        else
+            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, expected, ctl.sc, RED_BB, RED_RR_INIT, sh);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// K2': CSR SpMV on the reference's own arrays (drop-in mode), one thread per row, entries summed
+// sequentially in stored order like sprsAx (solvers.f90:54-61).
+// --------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_csr_spmv(const int n, const int *__restrict__ irow, const int *__restrict__ jcol, const double *__restrict__ valA,
+           const VecSet vs, const IterCtl ctl, double *partials, const int pstride, const unsigned expected)
+{
+    __shared__ double sh[32];
+    if (!spmv_guard<MODE>(ctl)) return;
+    double a0 = 0.0, a1 = 0.0;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) {
+        const int i1 = irow[r] - 1, i2 = irow[r + 1] - 1;
+        double s = 0.0;
+        for (int m = i1; m < i2; ++m) s = DADD(s, DMUL(__ldg(valA + m), vs.x[__ldg(jcol + m) - 1]));
+        row_epilogue<MODE>(s, r, vs.x[r], vs, a0, a1);
+    }
+    if (MODE != MODE_PLAIN) {
+        if (MODE == MODE_AP)
+            reduce_epilogue<1>(a0, 0.0, partials, pstride, blockIdx.x, expected, ctl.sc, RED_APR0, RED_APR0, sh);
+        else if (MODE == MODE_AS)
+            reduce_epilogue<2>(a0, a1, partials, pstride, blockIdx.x, expected, ctl.sc, RED_ASS, RED_ASAS, sh);
+        else
+            reduce_epilogue<2>(a0, a1, partials, pstride, blockIdx.x, expected, ctl.sc, RED_BB, RED_RR_INIT, sh);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// fused BiCGSTABwr vector kernels over the owned ranges of the segmented local vector
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long own_to_local(const SlabGeom &G, long long e)
+{
+    const int s = (int)(e >= G.own_cum[1]) + (int)(e >= G.own_cum[2]) + (int)(e >= G.own_cum[3]);
+    return G.own_off[s] + (e - G.own_cum[s]);
+}
+
+// K3: alpha = rr0/(AP,R0); S = R - alpha*AP; ||S||^2.            solvers.f90:31-34
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_s_update(const SlabGeom G, const double *__restrict__ R, const double *__restrict__ AP, double *__restrict__ S,
+           const IterCtl ctl, double *partials, const int pstride, const unsigned expected)
+{
+    __shared__ double sh[32];
+    Scal *sc = ctl.sc;
+    if (sc->done) return;
+    const int it = *ctl.iter_base + ctl.it_off;
+    const double rr0 = (it == 1) ? sc->red[RED_RR_INIT] : sc->rr0[it & 1];
+    const double alpha = rr0 / sc->red[RED_APR0];
+    if (is_block0()) sc->alpha = alpha;
+    double acc = 0.0;
+    const long long units = G.n_own / VEC;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < units;
+         q += (long long)gridDim.x * blockDim.x) {
+        const long long l = own_to_local(G, q * VEC);
+        if (VEC == 2) {
+            const double2 r = *reinterpret_cast<const double2 *>(R + l);
+            const double2 ap = *reinterpret_cast<const double2 *>(AP + l);
+            double2 s;
+            s.x = DSUB(r.x, DMUL(alpha, ap.x));
+            s.y = DSUB(r.y, DMUL(alpha, ap.y));
+            *reinterpret_cast<double2 *>(S + l) = s;
+            acc = DADD(acc, DMUL(s.x, s.x));
+            acc = DADD(acc, DMUL(s.y, s.y));
+        } else {
+            const double s = DSUB(R[l], DMUL(alpha, AP[l]));
+            S[l] = s;
+            acc = DADD(acc, DMUL(s, s));
+        }
+    }
+    reduce_epilogue<1>(acc, 0.0, partials, pstride, blockIdx.x, expected, sc, RED_SS, RED_SS, sh);
+}
+
+// K5: if ||S|| converged: X = X + alpha*P (solvers.f90:36).  Else omega = (AS,S)/(AS,AS);
+// X = X + alpha*P + omega*S; R = S - omega*AS; ||R||^2, (R,R0).   solvers.f90:40-44
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_xr_update(const SlabGeom G, double *__restrict__ X, const double *__restrict__ P, const double *__restrict__ S,
+            const double *__restrict__ AS, double *__restrict__ R, const double *__restrict__ R0,
+            const IterCtl ctl, double *partials, const int pstride, const unsigned expected)
+{
+    __shared__ double sh[32];
+    Scal *sc = ctl.sc;
+    if (sc->done) return;
+    const double alpha = sc->alpha;
+    const long long units = G.n_own / VEC;
+    const long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long qs = (long long)gridDim.x * blockDim.x;
+    if (s_converged(sc)) {
+        for (long long q = q0; q < units; q += qs) {
+            const long long l = own_to_local(G, q * VEC);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) X[l + v] = DADD(X[l + v], DMUL(alpha, P[l + v]));
+        }
+        return;
+    }
+    const double omega = sc->red[RED_ASS] / sc->red[RED_ASAS];
+    if (is_block0()) sc->omega = omega;
+    double a0 = 0.0, a1 = 0.0;
+    for (long long q = q0; q < units; q += qs) {
+        const long long l = own_to_local(G, q * VEC);
+        if (VEC == 2) {
+            double2 x = *reinterpret_cast<const double2 *>(X + l);
+            const double2 p = *reinterpret_cast<const double2 *>(P + l);
+            const double2 s = *reinterpret_cast<const double2 *>(S + l);
+            const double2 as = *reinterpret_cast<const double2 *>(AS + l);
+            const double2 r0 = *reinterpret_cast<const double2 *>(R0 + l);
+            double2 r;
+            x.x = DADD(DADD(x.x, DMUL(alpha, p.x)), DMUL(omega, s.x));
+            x.y = DADD(DADD(x.y, DMUL(alpha, p.y)), DMUL(omega, s.y));
+            r.x = DSUB(s.x, DMUL(omega, as.x));
+            r.y = DSUB(s.y, DMUL(omega, as.y));
+            *reinterpret_cast<double2 *>(X + l) = x;
+            *reinterpret_cast<double2 *>(R + l) = r;
+            a0 = DADD(a0, DMUL(r.x, r.x)); a0 = DADD(a0, DMUL(r.y, r.y));
+            a1 = DADD(a1, DMUL(r.x, r0.x)); a1 = DADD(a1, DMUL(r.y, r0.y));
+        } else {
+            const double s = S[l];
+            X[l] = DADD(DADD(X[l], DMUL(alpha, P[l])), DMUL(omega, s));
+            const double r = DSUB(s, DMUL(omega, AS[l]));
+            R[l] = r;
+            a0 = DADD(a0, DMUL(r, r));
+            a1 = DADD(a1, DMUL(r, R0[l]));
+        }
+    }
+    reduce_epilogue<2>(a0, a1, partials, pstride, blockIdx.x, expected, sc, RED_RR, RED_RR0N, sh);
+}
+
+// K6: exit tests, beta, P = R + beta*(P - omega*AP), restart.     solvers.f90:34-49
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_p_update(const SlabGeom G, double *__restrict__ P, const double *__restrict__ R, const double *__restrict__ AP,
+           double *__restrict__ R0, const IterCtl ctl)
+{
+    Scal *sc = ctl.sc;
+    if (sc->done) return;
+    const int it = *ctl.iter_base + ctl.it_off;
+    const double bnorm = sqrt(sc->red[RED_BB]);
+    if (s_converged(sc)) {                                              // exit taken at solvers.f90:34-38
+        if (is_block0()) { sc->exit_kind = 1; sc->final_iter = it; sc->done = 1; }
+        return;
+    }
+    if (sqrt(sc->red[RED_RR]) / bnorm < sc->tol) {                      // solvers.f90:43
+        if (is_block0()) { sc->exit_kind = 2; sc->final_iter = it; sc->done = 1; }
+        return;
+    }
+    const double rr0 = (it == 1) ? sc->red[RED_RR_INIT] : sc->rr0[it & 1];
+    const double rr0n = sc->red[RED_RR0N];
+    const double alpha = sc->alpha, omega = sc->omega;
+    const double beta = (alpha / omega) * rr0n / rr0;                   // solvers.f90:45
+    const bool restart = fabs(rr0n) / bnorm < sc->tol;                  // solvers.f90:47
+    if (is_block0()) {
+        sc->beta = beta;
+        // next (R,R0): after a restart R0 = R so it is ||R||^2, otherwise rr0_new (solvers.f90:31)
+        sc->rr0[(it + 1) & 1] = restart ? sc->red[RED_RR] : rr0n;
+        if (restart) sc->restarts += 1;
+    }
+    const long long units = G.n_own / VEC;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < units;
+         q += (long long)gridDim.x * blockDim.x) {
+        const long long l = own_to_local(G, q * VEC);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const double r = R[l + v];
+            if (restart) {
+                R0[l + v] = r;
+                P[l + v] = r;
+            } else {
+                P[l + v] = DADD(r, DMUL(beta, DSUB(P[l + v], DMUL(omega, AP[l + v]))));
+            }
+        }
+    }
+}
+
+__global__ void k_solver_reset(Scal *sc, int *iter_base, double tol, int itmax)
+{
+    for (int q = 0; q < 8; ++q) sc->red[q] = 0.0;
+    sc->rr0[0] = sc->rr0[1] = 0.0;
+    sc->alpha = sc->omega = sc->beta = 0.0;
+    sc->tol = tol; sc->itmax = itmax;
+    sc->done = 0; sc->final_iter = 0; sc->exit_kind = 0; sc->restarts = 0; sc->counter = 0u;
+    *iter_base = 0;
+}
+
+__global__ void k_iter_advance(int *iter_base, int by) { *iter_base += by; }
+
+// generic helpers
+__global__ void k_fill(double *p, long long n, double v)
+{
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x)
+        p[q] = v;
+}
