@@ -431,6 +431,7 @@ struct ec3d_handle {
     long long nU_send_lo = 0, nU_send_hi = 0;   // U entries in my first / last two planes
     // timing
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_t[2] = {nullptr, nullptr};
     double last_step_ms = 0.0, last_solve_ms = 0.0;
     long long launches = 0;
 };
@@ -520,6 +521,7 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     if (h->sol.h_flags) cudaFreeHost(h->sol.h_flags);
     if (h->h_src) cudaFreeHost(h->h_src);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return EC3D_OK;
@@ -551,6 +553,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     CUDA_TRY(cudaGetDevice(&h->device));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     for (auto &e : h->ev) CUDA_TRY(cudaEventCreate(&e));
+    for (auto &e : h->ev_t) CUDA_TRY(cudaEventCreate(&e));
 
     // ---- slab partition ----
     std::vector<long long> cpp(sdz, 0);          // conductor cells per plane
@@ -979,6 +982,27 @@ extern "C" int ec3d_step(ec3d_handle *h, const double *fun_vely, const double *v
         if (oob) { ec3d_set_error("a moved source cell fell outside the grid"); return EC3D_ERR_GEOMETRY; }
     }
     CUDA_TRY(cudaGetLastError());
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_timer_start(ec3d_handle *h)
+{
+    if (!h) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    CUDA_TRY(cudaEventRecord(h->ev_t[0], h->st));
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_timer_stop(ec3d_handle *h, double *ms)
+{
+    if (!h || !ms) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventRecord(h->ev_t[1], h->st));
+    CUDA_TRY(cudaEventSynchronize(h->ev_t[1]));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev_t[0], h->ev_t[1]));
+    *ms = t;
     return EC3D_OK;
 }
 

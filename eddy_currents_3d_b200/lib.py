@@ -19,7 +19,7 @@ EXPORTS = [
     "sprsbcgstabwr_", "ec3d_bicgstabwr_csr", "ec3d_csr_cache_clear", "ec3d_nccl_unique_id",
     "ec3d_create", "ec3d_destroy", "ec3d_sizes", "ec3d_assemble_csr", "ec3d_step", "ec3d_step_stage",
     "ec3d_get_fields", "ec3d_set_fields", "ec3d_get_source_cells", "ec3d_apply_operator",
-    "ec3d_solve_host", "ec3d_bench_kernel", "ec3d_counters", "ec3d_global_launch_count",
+    "ec3d_solve_host", "ec3d_bench_kernel", "ec3d_counters", "ec3d_timer_start", "ec3d_timer_stop", "ec3d_global_launch_count",
     "ec3d_last_error", "ec3d_version", "ec3d_partition_planes",
 ]
 
@@ -91,6 +91,10 @@ def load() -> C.CDLL:
     L.ec3d_bench_kernel.argtypes = [vp, i32, i32, i32, C.POINTER(dbl)]
     L.ec3d_counters.restype = C.c_int
     L.ec3d_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(dbl), C.POINTER(dbl)]
+    L.ec3d_timer_start.restype = C.c_int
+    L.ec3d_timer_start.argtypes = [vp]
+    L.ec3d_timer_stop.restype = C.c_int
+    L.ec3d_timer_stop.argtypes = [vp, C.POINTER(dbl)]
     L.ec3d_global_launch_count.restype = i64
     L.ec3d_last_error.restype = C.c_char_p
     L.ec3d_version.restype = C.c_char_p
@@ -277,6 +281,23 @@ class Handle:
         ms = C.c_double(0.0)
         _check(load().ec3d_bench_kernel(self._h, which, warm, reps, C.byref(ms)))
         return ms.value
+
+    def timer_start(self):
+        _check(load().ec3d_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0.0)
+        _check(load().ec3d_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def step_raw(self, fv_ptr: int, vv_ptr: int) -> int:
+        """ec3d_step on raw host pointers (pinned buffers in bench.py)."""
+        it = C.c_int32(0)
+        _check(load().ec3d_step(self._h, fv_ptr, vv_ptr, C.byref(it)))
+        return it.value
+
+    def get_fields_raw(self, u_ptr: int, j_ptr: int):
+        _check(load().ec3d_get_fields(self._h, u_ptr, j_ptr))
 
     def counters(self) -> dict:
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_double(), C.c_double()

@@ -206,3 +206,60 @@ def plate(N: int, variant: str = "A", tol: float = 5e-3, itmax: int = 10000,
                    geoPHYS=vv.astype(np.int8), geoPHYS_C=geoC, valPHYS=valPHYS,
                    cond_numdom=[1], cond_nod=nod, cond_valdom=valdom, sources=srcs, numMech=0,
                    evaluate_functions=evaluate_functions, name=f"plate({N}){variant}")
+
+
+# ---------------------------------------------------------------------------------------------
+# compact on-disk form of a Problem (tests/golden/*.npz): the voxel map, parameters and the
+# per-step source scalars tabulated on the reference's time grid (T = T + DT)
+# ---------------------------------------------------------------------------------------------
+def save_problem_npz(p: Problem, path: str, nsteps: Optional[int] = None) -> None:
+    ns = p.n_steps() if nsteps is None else nsteps
+    T, times = 0.0, []
+    for _ in range(ns):
+        times.append(T)
+        T = T + p.dt
+    tabs = [p.evaluate_functions(t) for t in times]
+    np.savez_compressed(
+        path, dims=np.array([p.sdx, p.sdy, p.sdz], np.int32), delta=p.delta, dt=p.dt, Time=p.Time, BND=p.BND,
+        tolerance=p.tolerance, itmax=p.itmax, geoPHYS=p.geoPHYS, valPHYS=p.valPHYS,
+        cond_numdom=np.array(p.cond_numdom, np.int32), cond_valdom=p.cond_valdom,
+        src_name=np.array([s.name for s in p.sources]), src_ex=np.array([s.ex for s in p.sources]),
+        src_nomsch=np.array([s.nomsch for s in p.sources], np.int32),
+        src_move=np.array([s.move for s in p.sources], np.int32).reshape(-1, 3),
+        src_numv=np.array([s.num_Vmech for s in p.sources], np.int32).reshape(-1, 3),
+        src_velv=np.array([s.vel_Vmech for s in p.sources], np.float64).reshape(-1, 3),
+        numMech=p.numMech, times=np.array(times),
+        fun_table=np.array([np.asarray(a[0], np.float64) for a in tabs]).reshape(ns, -1),
+        vmech_table=np.array([np.asarray(a[1], np.float64) for a in tabs]).reshape(ns, -1),
+        name=p.name)
+
+
+def load_problem_npz(path: str) -> Problem:
+    z = np.load(path, allow_pickle=False)
+    sdx, sdy, sdz = (int(x) for x in z["dims"])
+    nC = sdx * sdy * sdz
+    geoPHYS = z["geoPHYS"].astype(np.int8)
+    v = geoPHYS.astype(np.int64)
+    cond_numdom = [int(x) for x in z["cond_numdom"]]
+    geoC, nod = number_conductor(v, cond_numdom, nC)
+    sources = []
+    for i in range(len(z["src_ex"])):
+        ex, nomsch = str(z["src_ex"][i]), int(z["src_nomsch"][i])
+        sources.append(Source(name=str(z["src_name"][i]), ex=ex, nomsch=nomsch, nods=source_nodes(v, nomsch, ex, nC),
+                              move=z["src_move"][i].astype(np.int32), num_Vmech=z["src_numv"][i].astype(np.int32),
+                              vel_Vmech=z["src_velv"][i].astype(np.float64)))
+    times, ft, vt = z["times"], z["fun_table"], z["vmech_table"]
+    dt = float(z["dt"])
+
+    def evaluate_functions(t: float):
+        s = int(round(t / dt))
+        if s >= len(times) or abs(times[s] - t) > 1e-9 * max(1.0, abs(t)):
+            raise ValueError(f"time {t} is not on the tabulated grid of {path}")
+        return ft[s].copy(), vt[s].copy()
+
+    return Problem(sdx=sdx, sdy=sdy, sdz=sdz, delta=z["delta"].astype(np.float64), dt=dt, Time=float(z["Time"]),
+                   BND=z["BND"].astype(np.float64), tolerance=float(z["tolerance"]), itmax=int(z["itmax"]),
+                   geoPHYS=geoPHYS, geoPHYS_C=geoC, valPHYS=z["valPHYS"].astype(np.float64),
+                   cond_numdom=cond_numdom, cond_nod=nod, cond_valdom=z["cond_valdom"].astype(np.float64),
+                   sources=sources, numMech=int(z["numMech"]), evaluate_functions=evaluate_functions,
+                   name=str(z["name"]))

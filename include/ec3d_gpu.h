@@ -157,6 +157,11 @@ int ec3d_bench_kernel(ec3d_handle *h, int32_t which, int32_t warm, int32_t reps,
 int ec3d_counters(const ec3d_handle *h, int64_t *launches, int64_t *iterations,
                   double *last_step_ms, double *last_solve_ms);
 
+/* CUDA-event stopwatch on the library's stream (the stream every kernel of `h` is launched on):
+ * start synchronises the stream and records; stop records, waits and returns the elapsed ms. */
+int ec3d_timer_start(ec3d_handle *h);
+int ec3d_timer_stop(ec3d_handle *h, double *ms);
+
 int64_t ec3d_global_launch_count(void);
 
 const char *ec3d_last_error(void);
