@@ -30,7 +30,7 @@ struct EmitVisitor {
 // Per conductor cell: validity + flags.  flags bit0..2 = nAx,nAy,nAz; bit3..5 = nFix,nFiy,nFiz;
 // bit 6 = invalid geometry (the reference would STOP or read out of bounds).
 __global__ void k_classify_conductor(const SlabGeom G, const Coef cf, const int *__restrict__ geo,
-                                     const signed char *__restrict__ mat, const int nmat,
+                                     const signed char *__restrict__ mat, const int nmat, const int mat0,
                                      const int *__restrict__ cond_cells, const int ncond,
                                      unsigned char *__restrict__ flags, int *__restrict__ nbad)
 {
@@ -42,7 +42,7 @@ __global__ void k_classify_conductor(const SlabGeom G, const Coef cf, const int 
     int f = 0;
     const bool onb = (i == 0 || j == 0 || k == 0 || i == G.sdx - 1 || j == G.sdy - 1 || k == G.sdz - 1);
     const int m = mat[(long long)cell0 - (long long)(G.k0 - 2) * G.kdz];
-    if (onb || m < 1 || m > nmat) {
+    if (onb || m < 1 || m > nmat || m != mat0) {
         f = 64;
     } else {
         MatCoef mc{};   // values are irrelevant for classification
@@ -183,4 +183,24 @@ __global__ void k_compact_list(const SlabGeom G, const unsigned char *__restrict
     if (bit < 3) v = (int)(cell0 + 1 + bit * G.nC);
     else v = geo[(long long)cell0 - (long long)(G.k0 - 2) * G.kdz];
     list[pos[q]] = v;
+}
+
+// Class map of the fused SpMV (owned planes): 0 air / domain face, 1 interior conductor cell (all six
+// neighbours conductor), 2 conductor-surface cell (handled by the list kernel).
+__global__ void k_build_cls(const SlabGeom G, const int *__restrict__ cond_cells, const int ncond,
+                            const unsigned char *__restrict__ flags, unsigned char *__restrict__ cls,
+                            int *__restrict__ isslow)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncond) return;
+    const int slow = (flags[t] & 63) != 0;
+    cls[(long long)cond_cells[t] - (long long)G.k0 * G.kdz] = slow ? 2 : 1;
+    isslow[t] = slow;
+}
+
+__global__ void k_compact_cells(const int *__restrict__ cond_cells, const int ncond, const int *__restrict__ keep,
+                                const long long *__restrict__ pos, int *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ncond && keep[t]) out[pos[t]] = cond_cells[t];
 }

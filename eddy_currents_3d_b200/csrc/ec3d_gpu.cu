@@ -404,6 +404,13 @@ struct ec3d_handle {
     int *d_cond_cells = nullptr;
     int ncond = 0;
     unsigned char *d_flags = nullptr;
+    unsigned char *d_cls = nullptr;      // class map of the fused SpMV (owned planes)
+    int *d_slow_cells = nullptr;         // conductor-surface cells
+    int nslow = 0;
+    int mat0 = 0;
+    MatCoef mc0{};
+    bool fused = false;                  // k_stencil2_spmv usable (even sdx)
+    int minb = 2;
     double valdom = 0.0;
     int size_PHYS_C = 0;
     double dt = 0.0, delta[3] = {0, 0, 0}, tol = 0.0;
@@ -472,9 +479,28 @@ static int h_allreduce(ec3d_handle *h, int slot, int count)
     return EC3D_OK;
 }
 
+static int scan_i32_to_i64(cudaStream_t st, const int *in, long long *out, long long n, long long *total_host, long long &launches);
+
 template <int MODE>
 static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
 {
+    if (h->fused) {
+        Solver &s = h->sol;
+        const unsigned expected = (unsigned)(h->nblkAir + h->nblkCond);
+        const int fin = h->nblkCond == 0 ? 1 : 0;
+        if (h->minb == 3)
+            k_stencil2_spmv<MODE, 3><<<h->airGrid, dim3(32, 8), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
+                                                                           s.partials, s.pstride, expected, fin);
+        else
+            k_stencil2_spmv<MODE, 2><<<h->airGrid, dim3(32, 8), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
+                                                                           s.partials, s.pstride, expected, fin);
+        g_launches.fetch_add(1);
+        if (h->nblkCond == 0) return 1;
+        k_cond_spmv<MODE><<<h->nblkCond, 256, 0, h->st>>>(h->G, h->cf, h->d_mc, h->d_geo, h->d_mat, h->d_slow_cells, h->nslow,
+                                                          vs, ctl, s.partials, s.pstride, h->nblkAir, expected);
+        g_launches.fetch_add(1);
+        return 2;
+    }
     Solver &s = h->sol;
     const unsigned expected = (unsigned)(h->nblkAir + h->nblkCond);
     k_air_spmv<MODE, 32, 8><<<h->airGrid, dim3(32, 8), 0, h->st>>>(h->G, h->cf, h->d_geo, vs, ctl, h->zc, s.partials,
@@ -515,6 +541,7 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     if (h->sol.graph) cudaGraphExecDestroy(h->sol.graph);
     if (h->comm) ncclCommDestroy(h->comm);
     cudaFree(h->d_mc); cudaFree(h->d_geo); cudaFree(h->d_mat); cudaFree(h->d_cond_cells); cudaFree(h->d_flags);
+    cudaFree(h->d_cls); cudaFree(h->d_slow_cells);
     cudaFree(h->vecs); cudaFree(h->sol.sc); cudaFree(h->sol.iter_base); cudaFree(h->sol.partials);
     cudaFree(h->d_nod_ptr); cudaFree(h->d_nods); cudaFree(h->d_num_Vmech); cudaFree(h->d_comp);
     cudaFree(h->d_new_nodes); cudaFree(h->d_ms); cudaFree(h->d_fun_vely); cudaFree(h->d_vmech); cudaFree(h->d_oob);
@@ -637,6 +664,11 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
             CUDA_TRY(cudaMalloc(&h->d_flags, cells.size()));
         }
     }
+    if (Nc > 0) {
+        h->mat0 = cfg->geoPHYS[cfg->cond_nod[0] - 1];
+        if (h->mat0 < 1 || h->mat0 > cfg->nmat) { ec3d_set_error("conductor material id out of range"); return EC3D_ERR_ARG; }
+        build_matcoef(cfg->delta, cfg->dt, cfg->valPHYS + 5 * (h->mat0 - 1), h->mc0);
+    }
     // ---- vectors ----
     const int NV = 10;   // Uaf Jaf R R0 P AP S AS tmpx tmpy
     CUDA_TRY(cudaMalloc(&h->vecs, (size_t)G.ltot * NV * sizeof(double)));
@@ -681,8 +713,8 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         int *d_nbad = nullptr;
         CUDA_TRY(cudaMalloc(&d_nbad, sizeof(int)));
         CUDA_TRY(cudaMemset(d_nbad, 0, sizeof(int)));
-        k_classify_conductor<<<h->nblkCond, 256, 0, h->st>>>(G, h->cf, h->d_geo, h->d_mat, h->nmat, h->d_cond_cells,
-                                                             h->ncond, h->d_flags, d_nbad);
+        k_classify_conductor<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(G, h->cf, h->d_geo, h->d_mat, h->nmat, h->mat0,
+                                                                        h->d_cond_cells, h->ncond, h->d_flags, d_nbad);
         LAUNCHED(h->launches);
         int nbad = 0;
         CUDA_TRY(cudaMemcpyAsync(&nbad, d_nbad, sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -692,6 +724,50 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
             ec3d_set_error("%d conductor cells with invalid geometry (on a domain face, thinner than 3 cells at a free "
                            "face, or bad material id): the reference would STOP (EC3D.f90:717-720)", nbad);
             return EC3D_ERR_GEOMETRY;
+        }
+    }
+    // ---- fused SpMV: class map + conductor-surface list ----
+    {
+        const char *ef = getenv("EC3D_FUSED");
+        h->fused = (sdx % 2 == 0) && (kdz % 2 == 0) && !(ef && atoi(ef) == 0);
+        const char *eb = getenv("EC3D_MINB");
+        h->minb = (eb && atoi(eb) == 3) ? 3 : 2;
+    }
+    if (h->fused) {
+        CUDA_TRY(cudaMalloc(&h->d_cls, (size_t)G.nzl * kdz + 16));
+        CUDA_TRY(cudaMemsetAsync(h->d_cls, 0, (size_t)G.nzl * kdz + 16, h->st));
+        if (h->ncond) {
+            int *d_slow = nullptr; long long *d_pos = nullptr;
+            CUDA_TRY(cudaMalloc(&d_slow, (size_t)h->ncond * sizeof(int)));
+            CUDA_TRY(cudaMalloc(&d_pos, (size_t)h->ncond * sizeof(long long)));
+            k_build_cls<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(G, h->d_cond_cells, h->ncond, h->d_flags, h->d_cls, d_slow);
+            LAUNCHED(h->launches);
+            long long ns = 0;
+            int rc = scan_i32_to_i64(h->st, d_slow, d_pos, h->ncond, &ns, h->launches);
+            if (rc) return rc;
+            h->nslow = (int)ns;
+            if (ns) {
+                CUDA_TRY(cudaMalloc(&h->d_slow_cells, (size_t)ns * sizeof(int)));
+                k_compact_cells<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(h->d_cond_cells, h->ncond, d_slow, d_pos, h->d_slow_cells);
+                LAUNCHED(h->launches);
+            }
+            CUDA_TRY(cudaStreamSynchronize(h->st));
+            cudaFree(d_slow); cudaFree(d_pos);
+        }
+        const int tx = (sdx + 63) / 64, ty = (sdy + 7) / 8;
+        const int tiles = tx * ty;
+        const int want = (2 * 148 * 4 + tiles - 1) / tiles;
+        int zc = std::max(1, std::min(64, G.nzl / std::max(1, want)));
+        const char *ez = getenv("EC3D_ZC");
+        if (ez && atoi(ez) > 0) zc = atoi(ez);
+        h->zc = zc;
+        h->airGrid = dim3(tx, ty, (G.nzl + zc - 1) / zc);
+        h->nblkAir = tx * ty * (int)h->airGrid.z;
+        h->nblkCond = (h->nslow + 255) / 256;
+        if (h->nblkAir + h->nblkCond + 8 > s.pstride) {
+            cudaFree(s.partials);
+            s.pstride = h->nblkAir + h->nblkCond + 8;
+            CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 2 * sizeof(double)));
         }
     }
     // ---- sources ----
@@ -916,7 +992,7 @@ static int stage_rhs_pre(ec3d_handle *h)
     int rc = h_halo(h, h->Uaf);      // the U-row right-hand side reads Az(k+-1) of Uaf
     if (rc) return rc;
     if (h->ncond) {
-        k_rhs_pre<<<h->nblkCond, 256, 0, h->st>>>(h->G, h->cf, h->d_geo, h->d_cond_cells, h->ncond, h->d_flags, h->valdom,
+        k_rhs_pre<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(h->G, h->cf, h->d_geo, h->d_cond_cells, h->ncond, h->d_flags, h->valdom,
                                                   h->Uaf, h->Jaf);
         LAUNCHED(h->launches);
     }
@@ -937,7 +1013,7 @@ static int stage_solve(ec3d_handle *h, int32_t *iter)
 static int stage_rhs_post(ec3d_handle *h)
 {
     if (h->size_PHYS_C == 0 || h->ncond == 0) return EC3D_OK;
-    k_rhs_post<<<h->nblkCond, 256, 0, h->st>>>(h->G, h->d_cond_cells, h->ncond, h->d_flags, h->valdom, h->Uaf, h->Jaf);
+    k_rhs_post<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(h->G, h->d_cond_cells, h->ncond, h->d_flags, h->valdom, h->Uaf, h->Jaf);
     LAUNCHED(h->launches);
     return EC3D_OK;
 }
