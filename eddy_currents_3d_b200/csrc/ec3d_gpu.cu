@@ -411,6 +411,10 @@ struct ec3d_handle {
     MatCoef mc0{};
     bool fused = false;                  // k_stencil2_spmv usable (even sdx)
     int minb = 2;
+    int minb3 = 3;
+    int dbg = 0;                         // timing experiments only (EC3D_DBG)
+    int txt = 32;                        // threads along x of a stencil CTA (each owns 2 cells)
+    int kver = 3;                        // 3: one component per thread (k_stencil3_spmv), 2: k_stencil2_spmv
     double valdom = 0.0;
     int size_PHYS_C = 0;
     double dt = 0.0, delta[3] = {0, 0, 0}, tol = 0.0;
@@ -488,7 +492,21 @@ static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
         Solver &s = h->sol;
         const unsigned expected = (unsigned)(h->nblkAir + h->nblkCond);
         const int fin = h->nblkCond == 0 ? 1 : 0;
-        if (h->minb == 3)
+        if (h->kver == 3 && h->dbg && MODE == MODE_AS) {
+            const dim3 bd(h->txt, 256 / h->txt);
+#define DBGL(D) k_stencil3_spmv<MODE_AS, 3, D><<<h->airGrid, bd, 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc, s.partials, s.pstride, expected, fin)
+            switch (h->dbg) { case 1: DBGL(1); break; case 2: DBGL(2); break; case 3: DBGL(3); break; case 4: DBGL(4); break; case 7: DBGL(7); break; default: DBGL(5); break; }
+#undef DBGL
+        } else if (h->kver == 3 && h->minb3 == 4)
+            k_stencil3_spmv<MODE, 4><<<h->airGrid, dim3(h->txt, 256 / h->txt), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
+                                                                           s.partials, s.pstride, expected, fin);
+        else if (h->kver == 3 && h->minb3 == 2)
+            k_stencil3_spmv<MODE, 2><<<h->airGrid, dim3(h->txt, 256 / h->txt), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
+                                                                           s.partials, s.pstride, expected, fin);
+        else if (h->kver == 3)
+            k_stencil3_spmv<MODE, 3><<<h->airGrid, dim3(h->txt, 256 / h->txt), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
+                                                                           s.partials, s.pstride, expected, fin);
+        else if (h->minb == 3)
             k_stencil2_spmv<MODE, 3><<<h->airGrid, dim3(32, 8), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
                                                                            s.partials, s.pstride, expected, fin);
         else
@@ -732,6 +750,9 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         h->fused = (sdx % 2 == 0) && (kdz % 2 == 0) && !(ef && atoi(ef) == 0);
         const char *eb = getenv("EC3D_MINB");
         h->minb = (eb && atoi(eb) == 3) ? 3 : 2;
+        h->minb3 = (eb && atoi(eb) == 4) ? 4 : (eb && atoi(eb) == 2) ? 2 : 3;
+        const char *ed = getenv("EC3D_DBG");
+        h->dbg = ed ? atoi(ed) : 0;
     }
     if (h->fused) {
         CUDA_TRY(cudaMalloc(&h->d_cls, (size_t)G.nzl * kdz + 16));
@@ -754,14 +775,24 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
             CUDA_TRY(cudaStreamSynchronize(h->st));
             cudaFree(d_slow); cudaFree(d_pos);
         }
-        const int tx = (sdx + 63) / 64, ty = (sdy + 7) / 8;
-        const int tiles = tx * ty;
-        const int want = (2 * 148 * 4 + tiles - 1) / tiles;
-        int zc = std::max(1, std::min(64, G.nzl / std::max(1, want)));
+        const char *ek = getenv("EC3D_KVER");
+        h->kver = (ek && atoi(ek) == 2) ? 2 : 3;
+        {
+            const char *et = getenv("EC3D_TXT");
+            int txt = (et && atoi(et) > 0) ? atoi(et) : 32;
+            if (h->kver != 3 || (txt != 32 && txt != 64 && txt != 128 && txt != 256)) txt = 32;
+            h->txt = txt;
+        }
+        const int tx = (sdx + 2 * h->txt - 1) / (2 * h->txt), ty = (sdy + (256 / h->txt) - 1) / (256 / h->txt);
+        const int per_plane_chunk = tx * ty * (h->kver == 3 ? 3 : 1);
+        // aim for ~8 waves of 4 CTAs/SM so the tail is small; at most 32 planes per chunk
+        const int want = (8 * 148 * 4 + per_plane_chunk - 1) / per_plane_chunk;
+        int zc = std::max(1, std::min(32, G.nzl / std::max(1, want)));
         const char *ez = getenv("EC3D_ZC");
         if (ez && atoi(ez) > 0) zc = atoi(ez);
         h->zc = zc;
-        h->airGrid = dim3(tx, ty, (G.nzl + zc - 1) / zc);
+        const int nzch = (G.nzl + zc - 1) / zc;
+        h->airGrid = dim3(tx, ty, nzch * (h->kver == 3 ? 3 : 1));
         h->nblkAir = tx * ty * (int)h->airGrid.z;
         h->nblkCond = (h->nslow + 255) / 256;
         if (h->nblkAir + h->nblkCond + 8 > s.pstride) {

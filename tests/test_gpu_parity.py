@@ -1,0 +1,284 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libec3d_gpu.so and is compared with the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): sparsity index arrays bit-exact; fields within 1e-9 relative L2 at
+the reference's tolerance; iteration counts within 5% (observed: equal)."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DECKS, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_TOL = 1e-9      # north_star: relative L2 error of the A and U fields in fp64
+ITER_TOL = 0.05        # north_star: iteration counts within 5 %
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def iters_close(a, b):
+    return abs(a - b) <= max(1, int(np.ceil(ITER_TOL * b)))
+
+
+@pytest.fixture(scope="module")
+def plates():
+    from eddy_currents_3d_b200 import plate
+    return {v: plate(32, v) for v in "ABM"}
+
+
+def _check_assembly(lib, oracle_mod, p):
+    h = lib.Handle(p, device=0)
+    A = h.assemble_csr()
+    O = oracle_mod.Assembled(p)
+    assert O.rc == 0
+    assert A["num_nz"] == [O.num_nzX, O.num_nzY, O.num_nzZ, O.num_nzU, O.num_nz]
+    assert np.array_equal(A["irow"], O.irow)            # bit-exact index arrays
+    assert np.array_equal(A["jcol"], O.jcol)
+    assert np.array_equal(A["valA"].view(np.int64), O.valA.view(np.int64))   # bit-exact values
+    for nm in ("cel_bndX", "cel_bndY", "cel_bndZ", "cel_bndUx", "cel_bndUy", "cel_bndUz"):
+        assert np.array_equal(A[nm], getattr(O, nm)), nm
+    return h, O
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "M"])
+def test_assembly_bit_exact_plate(gpu_lib, oracle_mod, plates, variant):
+    h, _ = _check_assembly(gpu_lib, oracle_mod, plates[variant])
+    h.close()
+
+
+@pytest.mark.parametrize("deck", DECKS)
+def test_assembly_bit_exact_decks(gpu_lib, oracle_mod, deck_problems, deck):
+    h, O = _check_assembly(gpu_lib, oracle_mod, deck_problems[deck])
+    g = json.load(open(os.path.join(GOLDEN, deck + "_oracle.json")))
+    assert g["num_nz"][4] == O.num_nz
+    h.close()
+
+
+def test_assembly_odd_grid(gpu_lib, oracle_mod):
+    """Odd sdx exercises the scalar (non-vectorised) stencil and vector kernels."""
+    from eddy_currents_3d_b200.problem import Problem, number_conductor
+    sdx, sdy, sdz = 21, 17, 13
+    nC = sdx * sdy * sdz
+    v = np.full((sdz, sdy, sdx), 2, np.int64)
+    v[3:9, 4:12, 5:15] = 1
+    v[3:9, 6:9, 8:11] = 2
+    geoC, nod = number_conductor(v.reshape(-1), [1], nC)
+    C = 0.12566370964050292e-5 * 35.26e6
+    valPHYS = np.array([[1, C, C * 3, C * -2, C * 1.5], [1, 0, 0, 0, 0]], np.float64)
+    p = Problem(sdx=sdx, sdy=sdy, sdz=sdz, delta=np.array([0.002, 0.003, 0.0025]), dt=5e-4, Time=1e-3,
+                BND=np.array([[-0.9, -0.8], [-0.7, -0.95], [-0.85, -0.6]]), tolerance=5e-3, itmax=500,
+                geoPHYS=v.reshape(-1).astype(np.int8), geoPHYS_C=geoC, valPHYS=valPHYS, cond_numdom=[1],
+                cond_nod=nod, cond_valdom=np.array([2.0 * C / 5e-4]), sources=[], numMech=0,
+                evaluate_functions=lambda t: (np.zeros(0), np.zeros(0)))
+    h, O = _check_assembly(gpu_lib, oracle_mod, p)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, p.nCellsGlob)
+    y = h.apply_operator(x)
+    assert np.array_equal(y, oracle_mod.spmv(O.valA, O.irow, O.jcol, x))
+    h.close()
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_matrix_free_operator_equals_csr(gpu_lib, oracle_mod, plates, variant):
+    """The matrix-free stencil SpMV is bit-identical to the reference's sequential CSR row sums."""
+    p = plates[variant]
+    h = gpu_lib.Handle(p, device=0)
+    O = oracle_mod.Assembled(p)
+    rng = np.random.default_rng(11)
+    for scale in (1.0, 1e-6):
+        x = rng.uniform(-1, 1, p.nCellsGlob) * scale
+        assert np.array_equal(h.apply_operator(x), oracle_mod.spmv(O.valA, O.irow, O.jcol, x))
+    # linearity (size-independent property)
+    x1, x2 = rng.normal(size=p.nCellsGlob), rng.normal(size=p.nCellsGlob)
+    lhs = h.apply_operator(2.0 * x1 + x2)
+    rhs = 2.0 * h.apply_operator(x1) + h.apply_operator(x2)
+    assert rel(lhs, rhs) < 1e-13
+    h.close()
+
+
+@pytest.mark.parametrize("deck", DECKS)
+def test_matrix_free_operator_decks(gpu_lib, oracle_mod, deck_problems, deck):
+    p = deck_problems[deck]
+    h = gpu_lib.Handle(p, device=0)
+    O = oracle_mod.Assembled(p)
+    x = np.random.default_rng(2).uniform(-1, 1, p.nCellsGlob)
+    assert np.array_equal(h.apply_operator(x), oracle_mod.spmv(O.valA, O.irow, O.jcol, x))
+    h.close()
+
+
+def _rhs_of_first_step(oracle_mod, p):
+    run = oracle_mod.OracleRun(p)
+    run.step(solve=False)
+    return run, run.rhs.copy()
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_dropin_sprsBCGstabWR(gpu_lib, oracle_mod, plates, variant):
+    """The strict drop-in (gfortran symbol sprsbcgstabwr_, solvers.f90:3) on the reference's own
+    CSR arrays: same iter, x within 1e-9; Bnorm == 0 and itmax semantics."""
+    p = plates[variant]
+    run, b = _rhs_of_first_step(oracle_mod, p)
+    A = run.A
+    n = p.nCellsGlob
+    x_o, x_g = np.zeros(n), np.zeros(n)
+    it_o = oracle_mod.bicgstabwr(A.valA, A.irow, A.jcol, b, x_o, p.tolerance, p.itmax)
+    it_g = gpu_lib.sprsBCGstabWR(A.valA, A.irow, A.jcol, n, b, x_g, p.tolerance, p.itmax)
+    assert iters_close(it_g, it_o) and it_g == it_o
+    assert rel(x_g, x_o) < REL_L2_TOL
+    # warm start from the converged x: one iteration, like the reference
+    x2 = x_g.copy()
+    assert gpu_lib.sprsBCGstabWR(A.valA, A.irow, A.jcol, n, b, x2, 4 * p.tolerance, p.itmax) == \
+        oracle_mod.bicgstabwr(A.valA, A.irow, A.jcol, b, x_o.copy(), 4 * p.tolerance, p.itmax)
+    # Bnorm == 0: iter = 0, x untouched (solvers.f90:23)
+    x3 = np.full(n, 3.0)
+    assert gpu_lib.sprsBCGstabWR(A.valA, A.irow, A.jcol, n, np.zeros(n), x3, 1e-3, 100) == 0
+    assert np.all(x3 == 3.0)
+    # iter > itmax is tested before the increment: itmax+1 iterations (solvers.f90:25-29)
+    x4, x5 = np.zeros(n), np.zeros(n)
+    assert gpu_lib.sprsBCGstabWR(A.valA, A.irow, A.jcol, n, b, x4, 0.0, 4) == 5
+    import contextlib, io
+    fd = os.dup(1); dn = os.open(os.devnull, os.O_WRONLY); os.dup2(dn, 1)
+    try:
+        assert oracle_mod.bicgstabwr(A.valA, A.irow, A.jcol, b, x5, 0.0, 4) == 5
+    finally:
+        os.dup2(fd, 1); os.close(dn); os.close(fd)
+    assert rel(x4, x5) < REL_L2_TOL
+    gpu_lib.load().ec3d_csr_cache_clear()
+
+
+def test_matrix_free_solve_equals_dropin(gpu_lib, oracle_mod, plates):
+    p = plates["A"]
+    run, b = _rhs_of_first_step(oracle_mod, p)
+    n = p.nCellsGlob
+    x_o = np.zeros(n)
+    it_o = oracle_mod.bicgstabwr(run.A.valA, run.A.irow, run.A.jcol, b, x_o, p.tolerance, p.itmax)
+    h = gpu_lib.Handle(p, device=0)
+    x_m = np.zeros(n)
+    it_m = h.solve(b, x_m)
+    assert it_m == it_o and rel(x_m, x_o) < REL_L2_TOL
+    h.close()
+
+
+def _run_steps(lib, oracle_mod, p, nsteps, golden=None):
+    h = lib.Handle(p, device=0)
+    ref = oracle_mod.OracleRun(p)
+    for s in range(nsteps):
+        f, v = p.source_scalars(ref.T)
+        it_o = ref.step(f, v)
+        it_g = h.step(f, v)
+        U, J = h.get_fields()
+        assert iters_close(it_g, it_o), (s, it_g, it_o)
+        assert it_g == it_o, (s, it_g, it_o)
+        assert rel(U, ref.Uaf) < REL_L2_TOL, (s, rel(U, ref.Uaf))
+        assert rel(J, ref.Jaf) < REL_L2_TOL, (s, rel(J, ref.Jaf))
+        if ref.flag_move:
+            assert np.array_equal(h.source_cells(), ref.new_nodes[:len(h.source_cells())])
+        if golden is not None and s < len(golden["steps"]):
+            assert it_g == golden["steps"][s]["iter"]
+            idx = np.array(golden["sample_idx"])
+            assert rel(U[idx], np.array(golden["steps"][s]["U_sample"])) < 1e-8
+    c = h.counters()
+    assert c["launches"] > 0 and c["iterations"] == sum(ref.iters)
+    h.close()
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "M"])
+def test_timesteps_plate(gpu_lib, oracle_mod, plates, variant):
+    _run_steps(gpu_lib, oracle_mod, plates[variant], 5)
+
+
+@pytest.mark.parametrize("deck,nsteps", [("compare_to_Elmer", 3), ("ec_src_move_hole", 3), ("LIM", 6)])
+def test_timesteps_decks(gpu_lib, oracle_mod, deck_problems, deck, nsteps):
+    """The three shipped decks (static coil, moving coil over a plate with a hole, LIM)."""
+    g = json.load(open(os.path.join(GOLDEN, deck + "_oracle.json")))
+    _run_steps(gpu_lib, oracle_mod, deck_problems[deck], nsteps, golden=g)
+
+
+def test_moving_coil_clamps_at_the_wall(gpu_lib, oracle_mod):
+    """Constant-velocity coil driven into the x wall: cells stack at sdx-2 and movestop freezes the
+    motion (EC3D.f90:1052-1114), last-writer-wins scatter order."""
+    from eddy_currents_3d_b200 import plate
+    p = plate(32, "M")
+    for s in p.sources:
+        s.vel_Vmech = np.array([5 * 0.00333 / 1e-3, 0.0, 0.0])     # 5 cells per step
+    h = gpu_lib.Handle(p, device=0)
+    ref = oracle_mod.OracleRun(p)
+    for s in range(6):
+        f, v = p.source_scalars(ref.T)
+        ref.step(f, v, solve=False)
+        h.stage(0, f, v); h.stage(1); h.stage(3)
+        U, J = h.get_fields()
+        assert np.array_equal(h.source_cells(), ref.new_nodes[:len(h.source_cells())]), s
+        assert np.array_equal(J, ref.Jaf), s
+    h.close()
+
+
+def test_stage_rhs_bit_exact(gpu_lib, oracle_mod, plates):
+    """Source scatter + inertial sources / U-row right-hand side are bit-exact (no reductions)."""
+    p = plates["B"]
+    h = gpu_lib.Handle(p, device=0)
+    ref = oracle_mod.OracleRun(p)
+    rng = np.random.default_rng(4)
+    U0, J0 = rng.normal(size=p.nCellsGlob), rng.normal(size=p.nCellsGlob)
+    ref.Uaf[:], ref.Jaf[:] = U0, J0
+    h.set_fields(U0, J0)
+    f, v = p.source_scalars(0.0)
+    ref.step(f, v, solve=False)
+    h.stage(0, f, v); h.stage(1)
+    _, J = h.get_fields()
+    assert np.array_equal(J, ref.rhs)
+    h.stage(3)
+    U, J = h.get_fields()
+    assert np.array_equal(U, ref.Uaf) and np.array_equal(J, ref.Jaf)
+    h.close()
+
+
+def test_errors_are_loud(gpu_lib):
+    """Invalid geometry (reference: STOP) and unsupported configurations return error codes."""
+    from eddy_currents_3d_b200 import plate
+    from eddy_currents_3d_b200.problem import number_conductor
+    p = plate(32, "A")
+    v = p.geoPHYS.astype(np.int64).reshape(32, 32, 32).copy()
+    v[v == 1] = 6
+    v[10:12, 8:20, 8:20] = 1
+    p.geoPHYS = v.reshape(-1).astype(np.int8)
+    p.geoPHYS_C, p.cond_nod = number_conductor(v.reshape(-1), [1], p.nCells)
+    with pytest.raises(gpu_lib.Ec3dError) as e:
+        gpu_lib.Handle(p, device=0)
+    assert e.value.code == 3
+    q = plate(32, "A")
+    q.sources[0].ex = "D"                               # SRCZ -> 'D' -> the reference STOPs
+    with pytest.raises(gpu_lib.Ec3dError) as e:
+        gpu_lib.Handle(q, device=0)
+    assert e.value.code == 5
+
+
+def test_full_size_properties_plate256(gpu_lib):
+    """BASELINE full size (plate(256)): size-independent properties -- linearity of the operator,
+    zero row sums on interior air cells (constant vector -> 0), determinism run to run."""
+    from eddy_currents_3d_b200 import plate
+    p = plate(256, "A")
+    h = gpu_lib.Handle(p, device=0)
+    n, nC = p.nCellsGlob, p.nCells
+    rng = np.random.default_rng(0)
+    x1 = rng.normal(size=n)
+    y1 = h.apply_operator(x1)
+    assert np.array_equal(y1, h.apply_operator(x1))                  # deterministic
+    y2 = h.apply_operator(3.0 * x1)
+    assert rel(y2, 3.0 * y1) < 1e-14
+    ones = np.zeros(n); ones[:nC] = 1.0
+    y = h.apply_operator(ones)[:nC].reshape(256, 256, 256)
+    g = p.geoPHYS_C.reshape(256, 256, 256)
+    inner = np.zeros_like(g, bool); inner[1:-1, 1:-1, 1:-1] = True
+    assert np.max(np.abs(y[inner & (g == 0)])) < 1e-9 * 2.0 * 3 / 0.00333 ** 2
+    it = h.step()
+    assert 1 < it < 10000
+    U, J = h.get_fields()
+    assert np.isfinite(U).all() and np.isfinite(J).all()
+    h.close()

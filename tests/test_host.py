@@ -1,0 +1,130 @@
+"""CPU tests of the host side: expression evaluator / numeric prefixes (harness row N1), the .vxc
+loader against the golden problems, the slab partition, and the C-ABI library (loads, exports every
+symbol of include/ec3d_gpu.h; no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import DECKS, GOLDEN, ROOT
+
+
+def test_numeric_prefixes():
+    from eddy_currents_3d_b200.fparser import numeric
+    assert numeric("100m") == 1e-3 * 100.0          # utilites.f90:343-475
+    assert numeric("0.4m") == 1e-3 * 0.4
+    assert numeric("5m") == 1e-3 * 5.0
+    assert numeric("10000") == 10000.0
+    assert numeric("1k3") == 1e3 * 1.3
+    assert numeric("2meg") == 1e6 * 2.0
+    assert numeric("50") == 50.0
+    assert numeric("1e-3") == 1e-3
+
+
+def test_fparser_operator_split():
+    """m_fparser.f90:633-657: operators are split in the order + - * / ^ from the right, so
+    a*b/c = a*(b/c) and a+b-c = a+(b-c)."""
+    from eddy_currents_3d_b200.fparser import evalf
+    v = {"A": 3.0, "B": 7.0, "C": 0.3, "T": 0.01}
+    assert evalf("A*B/C", v) == 3.0 * (7.0 / 0.3)
+    assert evalf("A+B-C", v) == 3.0 + (7.0 - 0.3)
+    assert evalf("A-B+C", v) == (3.0 - 7.0) + 0.3
+    assert evalf("-A*B", v) == -(3.0 * 7.0)
+    assert evalf("A*COS(B*C*T)", v) == 3.0 * np.cos((7.0 * 0.3) * 0.01)
+    assert evalf("A*IMPL2(SIND(360*C*T))", v) == 3.0
+    assert evalf("-A*COSD(360*B*T+120)", v) == -(3.0 * np.cos(np.radians((360 * 7.0) * 0.01 + 120)))
+    assert evalf("2^3^2", v) == (2.0 ** 3.0) ** 2.0
+    assert evalf("1.5E+2+A", v) == 153.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference decks not present")
+@pytest.mark.parametrize("deck", DECKS)
+def test_vxc_loader_matches_golden(deck, deck_problems):
+    from eddy_currents_3d_b200 import load_vxc
+    p = load_vxc(f"/root/reference/src/{deck}.vxc")
+    q = deck_problems[deck]
+    assert (p.sdx, p.sdy, p.sdz) == (q.sdx, q.sdy, q.sdz)
+    assert np.array_equal(p.delta, q.delta) and p.dt == q.dt and p.Time == q.Time
+    assert p.tolerance == q.tolerance and p.itmax == q.itmax and np.array_equal(p.BND, q.BND)
+    assert np.array_equal(p.geoPHYS, q.geoPHYS) and np.array_equal(p.geoPHYS_C, q.geoPHYS_C)
+    assert np.array_equal(p.valPHYS, q.valPHYS) and np.array_equal(p.cond_valdom, q.cond_valdom)
+    assert len(p.sources) == len(q.sources) and p.numMech == q.numMech
+    for a, b in zip(p.sources, q.sources):
+        assert a.ex == b.ex and np.array_equal(a.nods, b.nods) and np.array_equal(a.num_Vmech, b.num_Vmech)
+    for s in (0, 1, 7):
+        T = 0.0
+        for _ in range(s):
+            T = T + p.dt
+        fa, va = p.source_scalars(T)
+        fb, vb = q.source_scalars(T)
+        assert np.array_equal(fa, fb) and np.array_equal(va, vb)
+
+
+def test_deck_parameters(deck_problems):
+    p = deck_problems["compare_to_Elmer"]
+    assert p.tolerance == 1e-3 * 5.0 and p.itmax == 10000 and p.dt == 1e-3 * 1.0
+    assert np.all(p.BND == -0.95)
+    # C = mu0*35.26e6 with the reference's MU0 literal (vxc2data.f90:402), valdom = 2C/dt (:461)
+    C = 0.12566370964050292e-5 * 35.26e6
+    assert p.valPHYS[0, 1] == C and p.cond_valdom[0] == 2.0 * C / p.dt
+    assert [len(s.nods) for s in p.sources] == [1944] * 4
+    q = deck_problems["LIM"]
+    assert len(q.sources) == 12 and q.numMech == 12 and q.cond_numdom == [13]
+    # node lists are in descending cell order (vxc2data.f90:656-752 pops a linked list)
+    assert all(np.all(np.diff(s.nods) < 0) for s in q.sources)
+
+
+def test_plate_generator():
+    from eddy_currents_3d_b200 import plate
+    p = plate(32, "A")
+    assert p.nCells0 == 32 ** 3 // 8 and p.nCellsGlob == 3 * 32 ** 3 + 32 ** 3 // 8     # n = 3.125 N^3
+    g = p.geoPHYS_C.reshape(32, 32, 32)
+    assert g[:, :, 0].max() == 0 and g[0].max() == 0 and g[-1].max() == 0             # >= 1 cell from faces
+    nz = g[g != 0]
+    assert np.array_equal(nz, 3 * 32 ** 3 + 1 + np.arange(nz.size))                    # k,j,i numbering
+    assert p.n_steps() == 11
+    assert plate(32, "B").valPHYS[0, 2] != 0.0 and plate(32, "M").sources[0].move[0] == 1
+
+
+def test_library_exports_every_header_symbol():
+    """The C-ABI library loads without a GPU and exports every function include/ec3d_gpu.h declares."""
+    from eddy_currents_3d_b200 import lib
+    L = lib.load()
+    hdr = open(os.path.join(ROOT, "include", "ec3d_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(ec3d_[a-z0-9_]+|sprsbcgstabwr_)\s*\(", hdr))
+    assert len(names) >= 20
+    for nm in sorted(names):
+        assert hasattr(L, nm), nm
+    assert set(lib.EXPORTS) == names
+    assert b"sm_100a" in L.ec3d_version()
+
+
+def test_no_cpu_fallback_in_product_path():
+    """The product package never imports, loads or executes anything under oracle/."""
+    pkg = os.path.join(ROOT, "eddy_currents_3d_b200")
+    for base, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")) or fn == "Makefile":
+                src = open(os.path.join(base, fn)).read()
+                assert not re.search(r"(import|from)\s+oracle|libec3d_oracle|ec3d_oracle\.h|orc_[a-z]", src), fn
+
+
+def test_partition_planes():
+    from eddy_currents_3d_b200 import lib
+    sdz = 64
+    cpp = np.zeros(sdz, np.int64)
+    cpp[8:24] = 64 * 64 // 2                               # conductor planes are heavier
+    for nr in (1, 2, 4, 8):
+        ks = lib.partition_planes(64, 64, sdz, cpp, nr)
+        assert ks[0] == 0 and ks[-1] == sdz and np.all(np.diff(ks) >= 2)
+        w = 152.0 * (3.0 * 64 * 64 + cpp) + 8.0 * 64 * 64 + 120.0 * cpp
+        loads = np.array([w[ks[r]:ks[r + 1]].sum() for r in range(nr)])
+        assert loads.max() / loads.mean() < 1.12, (nr, loads)
+    ks8 = lib.partition_planes(64, 64, sdz, cpp, 8)
+    counts = np.diff(ks8)
+    assert counts[1:3].max() <= counts[4:].min()           # heavier planes -> fewer planes per rank
+    with pytest.raises(lib.Ec3dError):
+        lib.partition_planes(64, 64, 6, np.zeros(6, np.int64), 8)
