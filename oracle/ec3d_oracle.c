@@ -12,6 +12,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+double orc_dot(const double *a, const double *b, int64_t n);
+static int g_dot_mode = 0;   /* see orc_set_dot_mode */
+
 /* ------------------------------------------------------------------------------------------ */
 /* gfortran intrinsics                                                                          */
 /* ------------------------------------------------------------------------------------------ */
@@ -20,6 +23,7 @@
  * trans-intrinsic.c): running scale + scaled sum of squares, one sequential pass. */
 double orc_norm2(const double *x, int64_t n)
 {
+    if (g_dot_mode == 1) return sqrt(orc_dot(x, x, n));
     double result = 0.0, scale = 1.0;
     for (int64_t i = 0; i < n; ++i) {
         if (x[i] != 0.0) {
@@ -37,9 +41,27 @@ double orc_norm2(const double *x, int64_t n)
     return scale * sqrt(result);
 }
 
+/* Summation-order switch, FOR SENSITIVITY EXPERIMENTS ONLY.  0 (default) = the reference's order
+ * (sequential).  1 = pairwise (recursive halving) dot products and sqrt(pairwise sum of squares)
+ * norms: an equally valid evaluation of the same formulas, used by the tests to measure how much
+ * the reference algorithm's output moves under reassociation of its reductions. */
+void orc_set_dot_mode(int mode) { g_dot_mode = mode; }
+
+static double pairwise_dot(const double *a, const double *b, int64_t n)
+{
+    if (n <= 8) {
+        double s = 0.0;
+        for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+        return s;
+    }
+    int64_t h = n / 2;
+    return pairwise_dot(a, b, h) + pairwise_dot(a + h, b + h, n - h);
+}
+
 /* DOT_PRODUCT: one sequential accumulator starting at 0. */
 double orc_dot(const double *a, const double *b, int64_t n)
 {
+    if (g_dot_mode == 1) return pairwise_dot(a, b, n);
     double s = 0.0;
     for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
     return s;

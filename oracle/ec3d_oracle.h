@@ -67,6 +67,9 @@ int orc_sprsBCGstabWR(const double *valA, const int32_t *irow, const int32_t *jc
 void orc_sprsAx(const double *valA, const int32_t *irow, const int32_t *jcol, int32_t n,
                 const double *v, double *y);
 
+/* Sensitivity experiments only: 0 = reference order (default), 1 = pairwise reductions. */
+void orc_set_dot_mode(int mode);
+
 /* gfortran NORM2 (scaled sum of squares) and sequential DOT_PRODUCT */
 double orc_norm2(const double *x, int64_t n);
 double orc_dot(const double *a, const double *b, int64_t n);

@@ -73,6 +73,8 @@ def lib():
                                         C.c_void_p, C.c_double, C.c_int32, C.POINTER(C.c_int32)]
         L.orc_sprsAx.restype = None
         L.orc_sprsAx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.orc_set_dot_mode.restype = None
+        L.orc_set_dot_mode.argtypes = [C.c_int]
         L.orc_norm2.restype = C.c_double
         L.orc_norm2.argtypes = [C.c_void_p, C.c_int64]
         L.orc_dot.restype = C.c_double
@@ -92,6 +94,11 @@ def lib():
 
 def _p(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data
+
+
+def set_dot_mode(mode: int) -> None:
+    """0 = the reference's sequential reductions (default); 1 = pairwise (sensitivity runs only)."""
+    lib().orc_set_dot_mode(int(mode))
 
 
 def norm2(x: np.ndarray) -> float:
