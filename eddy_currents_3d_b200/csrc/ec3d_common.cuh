@@ -4,10 +4,16 @@
 //   * z-slab: this rank owns planes k in [k0, k1) of the sdx*sdy*sdz grid (x fastest).
 //   * every Krylov / field vector is ONE allocation of `ltot` doubles made of four segments
 //       [ Ax : (nzl+2) planes | Ay : (nzl+2) planes | Az : (nzl+2) planes | U : nUlo+nUown+nUhi ]
-//     Each A segment carries one halo plane below and above the owned planes; the U segment
-//     carries the U unknowns of the two planes below / above (U is numbered in k,j,i order, so
-//     they are contiguous with the owned range).  The stencil indexes neighbours uniformly; halo
-//     entries are refreshed by the exchange that precedes each SpMV.
+//     Each A segment carries one halo plane below and above the owned planes.  The U segment is
+//     DENSE over the conductor's bounding box (ub_i0.., ub_j0.., ub_k0..; x extent padded to even):
+//     entry (i,j,k) sits at offU + (k-ub_kl0)*ub_pl + (j-ub_j0)*ub_nx + (i-ub_i0), planes
+//     [ub_kl0, ub_kl1) = box planes within [k0-2, k1+2) (two halo planes: one-sided z-gradients reach
+//     two cells).  Box cells that are not conductor cells are padding: they hold 0.0 in every
+//     vector and no kernel writes them, so BLAS-1 kernels can stream over the whole segment and
+//     the stencil reads U neighbours at fixed offsets (TMA tiles) instead of through geoPHYS_C.
+//     The reference's compact U numbering (k,j,i order over conductor cells) exists only at the
+//     C-ABI boundary (ec3d_get_fields / ec3d_set_fields pack and unpack).  Halo entries are
+//     refreshed by the exchange that precedes each SpMV.
 //   * geoPHYS_C / geoPHYS are stored for planes [k0-2, k1+2) (zero outside the domain).
 #pragma once
 #include <cstdint>
@@ -42,15 +48,23 @@ struct SlabGeom {
     long long segA;                // doubles per A segment (even)
     long long offU;                // 3*segA
     long long ltot;                // total local doubles
-    int gbase;                     // geoPHYS_C value g maps to local U index (g - gbase)
-    long long nUlo, nUown, nUhi;
-    long long u_first_global;      // 0-based global U number of local U index 0
+    // dense U box (global cell coordinates, half open); ub_nx even, ub_i0 even
+    int ub_i0, ub_j0, ub_k0, ub_nx, ub_ny, ub_nz;
+    int ub_kl0, ub_kl1;            // box planes stored by this rank: [ub_kl0, ub_kl1)
+    long long ub_pl;               // ub_nx * ub_ny
+    long long nUlo, nUown, nUhi;   // entries (padding included) of the halo-below / owned / halo-above planes
     // owned ranges inside the local vector: seg s starts at own_off[s], has own_len[s] entries
     long long own_off[4], own_len[4], own_cum[5];
     long long n_own;
     // global index (0-based, reference layout) of the first owned entry of each segment
     long long glob_off[4];
 };
+
+// Local index of the U unknown of cell (i,j,k) (0-based global coordinates) in the dense U box.
+__host__ __device__ __forceinline__ long long u_local(const SlabGeom &G, int i, int j, int k)
+{
+    return G.offU + (long long)(k - G.ub_kl0) * G.ub_pl + (long long)(j - G.ub_j0) * G.ub_nx + (i - G.ub_i0);
+}
 
 // Device-resident solver scalars (one per handle).
 struct Scal {

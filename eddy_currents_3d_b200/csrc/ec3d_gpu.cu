@@ -9,6 +9,9 @@
 #include "ec3d_common.cuh"
 #include "ec3d_kernels.cuh"
 #include "ec3d_step.cuh"
+#include "ec3d_tma.cuh"
+
+#include <cudaTypedefs.h>
 
 #include <nccl.h>
 
@@ -78,6 +81,7 @@ static void build_coef(const double delta[3], double dt, const double BND[3][2],
         const double tz = (m & 4) ? sz : 2.0 * sz;
         c.diag_b[m] = tx + ty + tz;
     }
+    c.diag_b[0] = c.diag_int;                               // index 0 = not on a domain face (branch-free lookup)
 }
 
 static void build_matcoef(const double delta[3], double dt, const double *vp /* valPHYS row */, MatCoef &m)
@@ -392,6 +396,8 @@ extern "C" void sprsbcgstabwr_(double *valA, int32_t *irow, int32_t *jcol, int32
 // ------------------------------------------------------------------------------------------
 // 2. GPU-resident handle
 // ------------------------------------------------------------------------------------------
+#define EC3D_NVEC 10   // Uaf Jaf R R0 P AP S AS tmpx tmpy
+
 struct ec3d_handle {
     int device = 0;
     cudaStream_t st = nullptr;
@@ -404,17 +410,17 @@ struct ec3d_handle {
     int *d_cond_cells = nullptr;
     int ncond = 0;
     unsigned char *d_flags = nullptr;
-    unsigned char *d_cls = nullptr;      // class map of the fused SpMV (owned planes)
-    int *d_slow_cells = nullptr;         // conductor-surface cells
-    int nslow = 0;
+    unsigned char *d_cls = nullptr;      // class bytes of the TMA SpMV (owned planes), see ec3d_tma.cuh
     int mat0 = 0;
     MatCoef mc0{};
-    bool fused = false;                  // k_stencil2_spmv usable (even sdx)
-    int minb = 2;
-    int minb3 = 3;
-    int dbg = 0;                         // timing experiments only (EC3D_DBG)
-    int txt = 32;                        // threads along x of a stencil CTA (each owns 2 cells)
-    int kver = 3;                        // 3: one component per thread (k_stencil3_spmv), 2: k_stencil2_spmv
+    bool tma = false;                    // k_spmv_tma usable (even sdx); else k_air_spmv + k_cond_spmv
+    int nstage = 4;                      // depth of the TMA ring (EC3D_NSTAGE = 3, 4, 5)
+    CUtensorMap tmA[EC3D_NVEC], tmU[EC3D_NVEC];   // per local vector: A part (4-D), dense U box (3-D)
+    CUtensorMap tmC;                     // class bytes (3-D, uint8)
+    int clsx = 0;                        // row pitch of d_cls (sdx rounded up to 16)
+    double *d_ucompact = nullptr;        // staging of the U block in the reference's compact numbering
+    long long u_glob0 = 0;               // 0-based global index of this rank's first U unknown
+    long long n_unknowns_own = 0;        // owned unknowns (without the padding of the dense U box)
     double valdom = 0.0;
     int size_PHYS_C = 0;
     double dt = 0.0, delta[3] = {0, 0, 0}, tol = 0.0;
@@ -485,41 +491,35 @@ static int h_allreduce(ec3d_handle *h, int slot, int count)
 
 static int scan_i32_to_i64(cudaStream_t st, const int *in, long long *out, long long n, long long *total_host, long long &launches);
 
+template <int MODE, int NSTAGE>
+static void launch_tma(ec3d_handle *h, int v, int vaux, const VecSet &vs, const IterCtl &ctl)
+{
+    Solver &s = h->sol;
+    k_spmv_tma<MODE, NSTAGE><<<h->airGrid, dim3(32, 8), tma::smem_bytes(NSTAGE), h->st>>>(
+        h->tmA[v], h->tmU[v], h->tmC, h->tmA[vaux], h->tmU[vaux], h->G, h->cf, h->mc0, vs, ctl, h->zc, s.partials,
+        s.pstride, (unsigned)h->nblkAir, 1);
+}
+
 template <int MODE>
 static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
 {
-    if (h->fused) {
-        Solver &s = h->sol;
-        const unsigned expected = (unsigned)(h->nblkAir + h->nblkCond);
-        const int fin = h->nblkCond == 0 ? 1 : 0;
-        if (h->kver == 3 && h->dbg && MODE == MODE_AS) {
-            const dim3 bd(h->txt, 256 / h->txt);
-#define DBGL(D) k_stencil3_spmv<MODE_AS, 3, D><<<h->airGrid, bd, 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc, s.partials, s.pstride, expected, fin)
-            switch (h->dbg) { case 1: DBGL(1); break; case 2: DBGL(2); break; case 3: DBGL(3); break; case 4: DBGL(4); break; case 7: DBGL(7); break; default: DBGL(5); break; }
-#undef DBGL
-        } else if (h->kver == 3 && h->minb3 == 4)
-            k_stencil3_spmv<MODE, 4><<<h->airGrid, dim3(h->txt, 256 / h->txt), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
-                                                                           s.partials, s.pstride, expected, fin);
-        else if (h->kver == 3 && h->minb3 == 2)
-            k_stencil3_spmv<MODE, 2><<<h->airGrid, dim3(h->txt, 256 / h->txt), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
-                                                                           s.partials, s.pstride, expected, fin);
-        else if (h->kver == 3)
-            k_stencil3_spmv<MODE, 3><<<h->airGrid, dim3(h->txt, 256 / h->txt), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
-                                                                           s.partials, s.pstride, expected, fin);
-        else if (h->minb == 3)
-            k_stencil2_spmv<MODE, 3><<<h->airGrid, dim3(32, 8), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
-                                                                           s.partials, s.pstride, expected, fin);
-        else
-            k_stencil2_spmv<MODE, 2><<<h->airGrid, dim3(32, 8), 0, h->st>>>(h->G, h->cf, h->mc0, h->d_cls, h->d_geo, vs, ctl, h->zc,
-                                                                           s.partials, s.pstride, expected, fin);
-        g_launches.fetch_add(1);
-        if (h->nblkCond == 0) return 1;
-        k_cond_spmv<MODE><<<h->nblkCond, 256, 0, h->st>>>(h->G, h->cf, h->d_mc, h->d_geo, h->d_mat, h->d_slow_cells, h->nslow,
-                                                          vs, ctl, s.partials, s.pstride, h->nblkAir, expected);
-        g_launches.fetch_add(1);
-        return 2;
-    }
     Solver &s = h->sol;
+    if (h->tma) {
+        // main path: one TMA-staged kernel produces every row (ec3d_tma.cuh)
+        const long long v = (vs.x - h->vecs) / h->G.ltot;
+        if (v < 0 || v >= EC3D_NVEC || h->vecs + v * h->G.ltot != vs.x) { ec3d_set_error("SpMV input is not a handle vector"); return -1; }
+        const double *auxp = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : vs.x;
+        long long va = (auxp - h->vecs) / h->G.ltot;
+        if (va < 0 || va >= EC3D_NVEC) va = v;            // (only used for an L2 prefetch)
+        switch (h->nstage) {
+        case 3: launch_tma<MODE, 3>(h, (int)v, (int)va, vs, ctl); break;
+        case 5: launch_tma<MODE, 5>(h, (int)v, (int)va, vs, ctl); break;
+        default: launch_tma<MODE, 4>(h, (int)v, (int)va, vs, ctl); break;
+        }
+        g_launches.fetch_add(1);
+        return 1;
+    }
+    // generic path (odd sdx): 7-point kernel for non-conductor cells + list kernel for conductor cells
     const unsigned expected = (unsigned)(h->nblkAir + h->nblkCond);
     k_air_spmv<MODE, 32, 8><<<h->airGrid, dim3(32, 8), 0, h->st>>>(h->G, h->cf, h->d_geo, vs, ctl, h->zc, s.partials,
                                                                   s.pstride, expected, h->nblkCond == 0 ? 1 : 0);
@@ -559,7 +559,7 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     if (h->sol.graph) cudaGraphExecDestroy(h->sol.graph);
     if (h->comm) ncclCommDestroy(h->comm);
     cudaFree(h->d_mc); cudaFree(h->d_geo); cudaFree(h->d_mat); cudaFree(h->d_cond_cells); cudaFree(h->d_flags);
-    cudaFree(h->d_cls); cudaFree(h->d_slow_cells);
+    cudaFree(h->d_cls); cudaFree(h->d_ucompact);
     cudaFree(h->vecs); cudaFree(h->sol.sc); cudaFree(h->sol.iter_base); cudaFree(h->sol.partials);
     cudaFree(h->d_nod_ptr); cudaFree(h->d_nods); cudaFree(h->d_num_Vmech); cudaFree(h->d_comp);
     cudaFree(h->d_new_nodes); cudaFree(h->d_ms); cudaFree(h->d_fun_vely); cudaFree(h->d_vmech); cudaFree(h->d_oob);
@@ -569,6 +569,81 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
+    return EC3D_OK;
+}
+
+// Tensor maps of every local vector: the A part as a 4-D tensor (x, y, local plane, component) with
+// a 68 x 10 x 1 x 3 box, the dense U box as a 3-D tensor with a 68 x 10 x 1 box; out-of-bounds
+// elements (domain faces, outside the U box, planes this rank does not store) are zero-filled.
+static int encode_tensor_maps(ec3d_handle *h)
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+    if (!enc) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (qr != cudaDriverEntryPointSuccess || !fn) { ec3d_set_error("cuTensorMapEncodeTiled not available"); return EC3D_ERR_CUDA; }
+        enc = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    }
+    const SlabGeom &G = h->G;
+    {
+        const cuuint64_t gdim[3] = {(cuuint64_t)h->clsx, (cuuint64_t)G.sdy, (cuuint64_t)G.nzl};
+        const cuuint64_t gstr[2] = {(cuuint64_t)h->clsx, (cuuint64_t)h->clsx * G.sdy};
+        const cuuint32_t box[3] = {tma::TX, tma::TY, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = enc(&h->tmC, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->d_cls, gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { ec3d_set_error("cuTensorMapEncodeTiled(class map) failed: %d", (int)r); return EC3D_ERR_CUDA; }
+    }
+    for (int v = 0; v < EC3D_NVEC; ++v) {
+        double *base = h->vecs + (long long)v * G.ltot;
+        {
+            const cuuint64_t gdim[4] = {(cuuint64_t)G.sdx, (cuuint64_t)G.sdy, (cuuint64_t)(G.nzl + 2), 3};
+            const cuuint64_t gstr[3] = {(cuuint64_t)G.sdx * 8, (cuuint64_t)G.kdz * 8, (cuuint64_t)G.segA * 8};
+            const cuuint32_t box[4] = {tma::BW, tma::BH, 1, 3};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            const CUresult r = enc(&h->tmA[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { ec3d_set_error("cuTensorMapEncodeTiled(A part) failed: %d", (int)r); return EC3D_ERR_CUDA; }
+        }
+        const int nst = G.ub_kl1 - G.ub_kl0;
+        if (nst > 0) {
+            const cuuint64_t gdim[3] = {(cuuint64_t)G.ub_nx, (cuuint64_t)G.ub_ny, (cuuint64_t)nst};
+            const cuuint64_t gstr[2] = {(cuuint64_t)G.ub_nx * 8, (cuuint64_t)G.ub_pl * 8};
+            const cuuint32_t box[3] = {tma::BW, tma::BH, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = enc(&h->tmU[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base + G.offU, gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { ec3d_set_error("cuTensorMapEncodeTiled(U box) failed: %d", (int)r); return EC3D_ERR_CUDA; }
+        } else {
+            h->tmU[v] = h->tmA[v];     // never dereferenced: no tile needs U
+        }
+    }
+    return EC3D_OK;
+}
+
+template <int MODE, int NSTAGE>
+static cudaError_t set_attr_one()
+{
+    return cudaFuncSetAttribute(k_spmv_tma<MODE, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::smem_bytes(NSTAGE));
+}
+template <int NSTAGE>
+static cudaError_t set_attr_modes()
+{
+    cudaError_t e;
+    if ((e = set_attr_one<MODE_PLAIN, NSTAGE>()) != cudaSuccess) return e;
+    if ((e = set_attr_one<MODE_AP, NSTAGE>()) != cudaSuccess) return e;
+    if ((e = set_attr_one<MODE_AS, NSTAGE>()) != cudaSuccess) return e;
+    return set_attr_one<MODE_INIT, NSTAGE>();
+}
+static int set_tma_smem_attr()
+{
+    CUDA_TRY(set_attr_modes<3>());
+    CUDA_TRY(set_attr_modes<4>());
+    CUDA_TRY(set_attr_modes<5>());
     return EC3D_OK;
 }
 
@@ -613,27 +688,46 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     memset(&G, 0, sizeof(G));
     G.sdx = sdx; G.sdy = sdy; G.sdz = sdz; G.kdz = (int)kdz; G.nC = nC;
     G.k0 = kstart[h->rank]; G.k1 = kstart[h->rank + 1]; G.nzl = G.k1 - G.k0;
-    std::vector<long long> ucum(sdz + 1, 0);      // U numbering is k-major for one domain
-    for (int k = 0; k < sdz; ++k) ucum[k + 1] = ucum[k] + cpp[k];
-    auto clampk = [&](int k) { return std::min(std::max(k, 0), sdz); };
-    const long long u_lo = ucum[clampk(G.k0 - 2)], u_own0 = ucum[G.k0], u_own1 = ucum[G.k1], u_hi = ucum[clampk(G.k1 + 2)];
+    // dense U box = bounding box of the conductor (x range padded to even offsets), identical on every rank
+    int bi0 = sdx, bi1 = -1, bj0 = sdy, bj1 = -1, bk0 = sdz, bk1 = -1;
+    for (long long q = 0; q < Nc; ++q) {
+        const long long c0 = cfg->cond_nod[q] - 1;
+        if (c0 < 0 || c0 >= nC) { ec3d_set_error("conductor cell number out of range"); return EC3D_ERR_ARG; }
+        const int k = (int)(c0 / kdz), rem = (int)(c0 - (long long)k * kdz), j = rem / sdx, i = rem - j * sdx;
+        bi0 = std::min(bi0, i); bi1 = std::max(bi1, i);
+        bj0 = std::min(bj0, j); bj1 = std::max(bj1, j);
+        bk0 = std::min(bk0, k); bk1 = std::max(bk1, k);
+    }
+    if (Nc > 0) {
+        G.ub_i0 = bi0 & ~1; G.ub_nx = ((bi1 + 1 - G.ub_i0) + 1) & ~1;
+        G.ub_j0 = bj0; G.ub_ny = bj1 + 1 - bj0;
+        G.ub_k0 = bk0; G.ub_nz = bk1 + 1 - bk0;
+    }
+    G.ub_pl = (long long)G.ub_nx * G.ub_ny;
+    // entries of the dense box below plane k (U is k-major, so a slab owns a contiguous range)
+    auto ucum = [&](int k) { return G.ub_pl * (long long)std::min(std::max(k - G.ub_k0, 0), G.ub_nz); };
+    auto boxk = [&](int k) { return G.ub_k0 + std::min(std::max(k - G.ub_k0, 0), G.ub_nz); };
+    G.ub_kl0 = boxk(G.k0 - 2); G.ub_kl1 = boxk(G.k1 + 2);
+    const long long u_lo = ucum(G.k0 - 2), u_own0 = ucum(G.k0), u_own1 = ucum(G.k1), u_hi = ucum(G.k1 + 2);
     G.nUlo = u_own0 - u_lo; G.nUown = u_own1 - u_own0; G.nUhi = u_hi - u_own1;
-    h->nU_send_lo = ucum[clampk(G.k0 + 2)] - u_own0;
-    h->nU_send_hi = u_own1 - ucum[clampk(G.k1 - 2)];
+    h->nU_send_lo = ucum(G.k0 + 2) - u_own0;
+    h->nU_send_hi = u_own1 - ucum(G.k1 - 2);
     long long segA = (long long)(G.nzl + 2) * kdz;
     segA += segA & 1;
     G.segA = segA; G.offU = 3 * segA;
-    // keep the owned U range 16-byte aligned when possible: pad the front if nUlo is odd
-    long long upad = G.nUlo & 1;
-    G.offU += upad;
     G.ltot = G.offU + G.nUlo + G.nUown + G.nUhi + 2;
-    G.u_first_global = u_lo;
-    G.gbase = (int)(3 * nC + 1 + u_lo);
+    G.ltot += G.ltot & 1;
     for (int c = 0; c < 3; ++c) {
         G.own_off[c] = c * segA + kdz; G.own_len[c] = (long long)G.nzl * kdz;
         G.glob_off[c] = c * nC + (long long)G.k0 * kdz;
     }
-    G.own_off[3] = G.offU + G.nUlo; G.own_len[3] = G.nUown; G.glob_off[3] = 3 * nC + u_own0;
+    G.own_off[3] = G.offU + G.nUlo; G.own_len[3] = G.nUown;
+    {
+        long long below = 0;                      // conductor cells in planes below k0 (compact numbering)
+        for (int k = 0; k < G.k0; ++k) below += cpp[k];
+        h->u_glob0 = 3 * nC + below;
+        G.glob_off[3] = h->u_glob0;
+    }
     G.own_cum[0] = 0;
     for (int c = 0; c < 4; ++c) G.own_cum[c + 1] = G.own_cum[c] + G.own_len[c];
     G.n_own = G.own_cum[4];
@@ -663,23 +757,27 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     // ---- owned conductor cells (k,j,i order; the list is ascending like PHYS_C%nod) ----
     {
         std::vector<int> cells;
-        cells.reserve((size_t)G.nUown);
+        long long own_cond = 0;
+        for (int k = G.k0; k < G.k1; ++k) own_cond += cpp[k];
+        cells.reserve((size_t)own_cond);
         for (long long q = 0; q < Nc; ++q) {
             const long long c0 = cfg->cond_nod[q] - 1;
             const int k = (int)(c0 / kdz);
             if (k >= G.k0 && k < G.k1) cells.push_back((int)c0);
         }
         if (!std::is_sorted(cells.begin(), cells.end())) { ec3d_set_error("PHYS_C%%nod must be ascending"); return EC3D_ERR_ARG; }
-        if ((long long)cells.size() != G.nUown) { ec3d_set_error("conductor list inconsistent with planes"); return EC3D_ERR_ARG; }
+        if ((long long)cells.size() != own_cond) { ec3d_set_error("conductor list inconsistent with planes"); return EC3D_ERR_ARG; }
         // geoPHYS_C must number the conductor cells consecutively in k,j,i order
         for (size_t q = 0; q < cells.size(); q += std::max<size_t>(1, cells.size() / 64)) {
-            if (cfg->geoPHYS_C[cells[q]] != (int)(3 * nC + 1 + u_own0 + (long long)q)) { ec3d_set_error("geoPHYS_C numbering is not k,j,i ordered"); return EC3D_ERR_ARG; }
+            if (cfg->geoPHYS_C[cells[q]] != (int)(h->u_glob0 + 1 + (long long)q)) { ec3d_set_error("geoPHYS_C numbering is not k,j,i ordered"); return EC3D_ERR_ARG; }
         }
         h->ncond = (int)cells.size();
+        h->n_unknowns_own = 3LL * G.nzl * kdz + h->ncond;
         if (h->ncond) {
             CUDA_TRY(cudaMalloc(&h->d_cond_cells, cells.size() * sizeof(int)));
             CUDA_TRY(cudaMemcpy(h->d_cond_cells, cells.data(), cells.size() * sizeof(int), cudaMemcpyHostToDevice));
             CUDA_TRY(cudaMalloc(&h->d_flags, cells.size()));
+            CUDA_TRY(cudaMalloc(&h->d_ucompact, cells.size() * sizeof(double)));
         }
     }
     if (Nc > 0) {
@@ -688,7 +786,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         build_matcoef(cfg->delta, cfg->dt, cfg->valPHYS + 5 * (h->mat0 - 1), h->mc0);
     }
     // ---- vectors ----
-    const int NV = 10;   // Uaf Jaf R R0 P AP S AS tmpx tmpy
+    const int NV = EC3D_NVEC;
     CUDA_TRY(cudaMalloc(&h->vecs, (size_t)G.ltot * NV * sizeof(double)));
     CUDA_TRY(cudaMemset(h->vecs, 0, (size_t)G.ltot * NV * sizeof(double)));
     Solver &s = h->sol;
@@ -744,60 +842,42 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
             return EC3D_ERR_GEOMETRY;
         }
     }
-    // ---- fused SpMV: class map + conductor-surface list ----
+    // ---- TMA SpMV: class bytes, tensor maps, launch shape ----
     {
-        const char *ef = getenv("EC3D_FUSED");
-        h->fused = (sdx % 2 == 0) && (kdz % 2 == 0) && !(ef && atoi(ef) == 0);
-        const char *eb = getenv("EC3D_MINB");
-        h->minb = (eb && atoi(eb) == 3) ? 3 : 2;
-        h->minb3 = (eb && atoi(eb) == 4) ? 4 : (eb && atoi(eb) == 2) ? 2 : 3;
-        const char *ed = getenv("EC3D_DBG");
-        h->dbg = ed ? atoi(ed) : 0;
+        const char *ef = getenv("EC3D_TMA");
+        h->tma = (sdx % 2 == 0) && !(ef && atoi(ef) == 0);
+        const char *en = getenv("EC3D_NSTAGE");
+        h->nstage = (en && (atoi(en) == 3 || atoi(en) == 5)) ? atoi(en) : 4;
     }
-    if (h->fused) {
-        CUDA_TRY(cudaMalloc(&h->d_cls, (size_t)G.nzl * kdz + 16));
-        CUDA_TRY(cudaMemsetAsync(h->d_cls, 0, (size_t)G.nzl * kdz + 16, h->st));
+    if (h->tma) {
+        h->clsx = (sdx + 15) & ~15;
+        const size_t cbytes = (size_t)G.nzl * sdy * h->clsx;
+        CUDA_TRY(cudaMalloc(&h->d_cls, cbytes));
+        CUDA_TRY(cudaMemsetAsync(h->d_cls, 0, cbytes, h->st));
         if (h->ncond) {
-            int *d_slow = nullptr; long long *d_pos = nullptr;
-            CUDA_TRY(cudaMalloc(&d_slow, (size_t)h->ncond * sizeof(int)));
-            CUDA_TRY(cudaMalloc(&d_pos, (size_t)h->ncond * sizeof(long long)));
-            k_build_cls<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(G, h->d_cond_cells, h->ncond, h->d_flags, h->d_cls, d_slow);
+            k_build_cls2<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(G, h->d_geo, h->d_cond_cells, h->ncond, h->d_cls, h->clsx);
             LAUNCHED(h->launches);
-            long long ns = 0;
-            int rc = scan_i32_to_i64(h->st, d_slow, d_pos, h->ncond, &ns, h->launches);
-            if (rc) return rc;
-            h->nslow = (int)ns;
-            if (ns) {
-                CUDA_TRY(cudaMalloc(&h->d_slow_cells, (size_t)ns * sizeof(int)));
-                k_compact_cells<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(h->d_cond_cells, h->ncond, d_slow, d_pos, h->d_slow_cells);
-                LAUNCHED(h->launches);
-            }
-            CUDA_TRY(cudaStreamSynchronize(h->st));
-            cudaFree(d_slow); cudaFree(d_pos);
         }
-        const char *ek = getenv("EC3D_KVER");
-        h->kver = (ek && atoi(ek) == 2) ? 2 : 3;
-        {
-            const char *et = getenv("EC3D_TXT");
-            int txt = (et && atoi(et) > 0) ? atoi(et) : 32;
-            if (h->kver != 3 || (txt != 32 && txt != 64 && txt != 128 && txt != 256)) txt = 32;
-            h->txt = txt;
-        }
-        const int tx = (sdx + 2 * h->txt - 1) / (2 * h->txt), ty = (sdy + (256 / h->txt) - 1) / (256 / h->txt);
-        const int per_plane_chunk = tx * ty * (h->kver == 3 ? 3 : 1);
-        // aim for ~8 waves of 4 CTAs/SM so the tail is small; at most 32 planes per chunk
-        const int want = (8 * 148 * 4 + per_plane_chunk - 1) / per_plane_chunk;
-        int zc = std::max(1, std::min(32, G.nzl / std::max(1, want)));
+        int rc = encode_tensor_maps(h);
+        if (rc) return rc;
+        rc = set_tma_smem_attr();
+        if (rc) return rc;
+        const int tx = (sdx + tma::TX - 1) / tma::TX, ty = (sdy + tma::TY - 1) / tma::TY;
+        const int tiles = tx * ty;
+        // z chunks: about two rounds of 2 CTAs/SM keep the z-halo re-reads (2 planes per chunk) small
+        // while leaving enough CTAs in the last round to keep HBM busy
+        const int nzch_want = std::max(1, (2 * 2 * 148 + tiles / 2) / tiles);
+        int zc = std::max(std::min(G.nzl, 4), (G.nzl + nzch_want - 1) / nzch_want);
         const char *ez = getenv("EC3D_ZC");
         if (ez && atoi(ez) > 0) zc = atoi(ez);
         h->zc = zc;
         const int nzch = (G.nzl + zc - 1) / zc;
-        h->airGrid = dim3(tx, ty, nzch * (h->kver == 3 ? 3 : 1));
-        h->nblkAir = tx * ty * (int)h->airGrid.z;
-        h->nblkCond = (h->nslow + 255) / 256;
-        if (h->nblkAir + h->nblkCond + 8 > s.pstride) {
+        h->airGrid = dim3(tx, ty, nzch);
+        h->nblkAir = tiles * nzch;
+        h->nblkCond = 0;
+        if (h->nblkAir + 8 > s.pstride) {
             cudaFree(s.partials);
-            s.pstride = h->nblkAir + h->nblkCond + 8;
+            s.pstride = h->nblkAir + 8;
             CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 2 * sizeof(double)));
         }
     }
@@ -890,27 +970,40 @@ extern "C" int ec3d_sizes(const ec3d_handle *h, int64_t *nCells, int64_t *nCells
     if (nCellsGlob) *nCellsGlob = h->nGlob;
     if (k0) *k0 = h->G.k0;
     if (k1) *k1 = h->G.k1;
-    if (n_owned) *n_owned = h->G.n_own;
+    if (n_owned) *n_owned = h->n_unknowns_own;
     return EC3D_OK;
 }
 
-// copies between the reference layout (full-length host vectors) and the local layout
+// copies between the reference layout (full-length host vectors) and the local layout; the U block
+// is packed / unpacked between the reference's compact numbering and the dense U box on the device
 static int copy_in(ec3d_handle *h, double *dst_local, const double *src_global)
 {
     const SlabGeom &G = h->G;
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < 3; ++c)
         if (G.own_len[c])
             CUDA_TRY(cudaMemcpyAsync(dst_local + G.own_off[c], src_global + G.glob_off[c], (size_t)G.own_len[c] * sizeof(double),
                                      cudaMemcpyHostToDevice, h->st));
+    if (h->ncond) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_ucompact, src_global + h->u_glob0, (size_t)h->ncond * sizeof(double),
+                                 cudaMemcpyHostToDevice, h->st));
+        k_u_unpack<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(G, h->d_cond_cells, h->ncond, h->d_ucompact, dst_local);
+        LAUNCHED(h->launches);
+    }
     return h_halo(h, dst_local);
 }
 static int copy_out(ec3d_handle *h, double *dst_global, const double *src_local)
 {
     const SlabGeom &G = h->G;
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < 3; ++c)
         if (G.own_len[c])
             CUDA_TRY(cudaMemcpyAsync(dst_global + G.glob_off[c], src_local + G.own_off[c], (size_t)G.own_len[c] * sizeof(double),
                                      cudaMemcpyDeviceToHost, h->st));
+    if (h->ncond) {
+        k_u_pack<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(G, h->d_cond_cells, h->ncond, src_local, h->d_ucompact);
+        LAUNCHED(h->launches);
+        CUDA_TRY(cudaMemcpyAsync(dst_global + h->u_glob0, h->d_ucompact, (size_t)h->ncond * sizeof(double),
+                                 cudaMemcpyDeviceToHost, h->st));
+    }
     return EC3D_OK;
 }
 
@@ -1281,6 +1374,9 @@ extern "C" int ec3d_bench_kernel(ec3d_handle *h, int32_t which, int32_t warm, in
         total += t;
     }
     *ms = total / reps;
+    // the fill also wrote the padding of the dense U box: restore the all-zero state of the work vectors
+    CUDA_TRY(cudaMemsetAsync(s.R, 0, (size_t)G.ltot * 8 * sizeof(double), h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
     CUDA_TRY(cudaGetLastError());
     return EC3D_OK;
 }

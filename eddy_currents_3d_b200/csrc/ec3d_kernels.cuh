@@ -241,54 +241,19 @@ k_air_spmv(const SlabGeom G, const Coef cf, const int *__restrict__ geo, const V
 }
 
 // --------------------------------------------------------------------------------------------
-// K2 (main path): fused matrix-free SpMV.  Each thread owns TWO x-adjacent cells of an (i,j)
-// column and marches over `zc` planes: the k-1 / k / k+1 values of the three components live in
-// registers, plane k+2 is prefetched one iteration ahead (16-byte loads), x/y neighbours come
-// through L1.  Per cell the 1-byte class map selects
-//   0  air or domain-face cell ...... the reference's boundary / interior Laplacian rows
-//   1  interior conductor cell ...... convection + 2C/dt + central grad-U rows and the 13-entry
-//                                     U row (EC3D.f90:649-680, 917-922), all gathers inline
-//   2  conductor-surface cell ....... skipped here; k_cond_spmv handles the (short) surface list
-// Rows are summed in ascending column order with unfused mul/add, so results equal the CSR sums.
+// 16-byte helpers and the pair epilogue shared by the SpMV kernels that own two x-adjacent cells
+// per thread (ec3d_tma.cuh).
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 
-template <int MODE>
-__device__ __forceinline__ void pair_epilogue(double ya, double yb, bool wa, bool wb, long long idx, double xa,
-                                              double xb, const VecSet &vs, double &a0, double &a1)
-{
-    if (wa && wb) {
-        if (MODE == MODE_PLAIN) {
-            st2(vs.y + idx, ya, yb);
-        } else if (MODE == MODE_AP) {
-            st2(vs.y + idx, ya, yb);
-            const double2 r0 = ld2(vs.r0 + idx);
-            a0 = DADD(a0, DMUL(ya, r0.x));
-            a0 = DADD(a0, DMUL(yb, r0.y));
-        } else if (MODE == MODE_AS) {
-            st2(vs.y + idx, ya, yb);
-            a0 = DADD(a0, DMUL(ya, xa)); a1 = DADD(a1, DMUL(ya, ya));
-            a0 = DADD(a0, DMUL(yb, xb)); a1 = DADD(a1, DMUL(yb, yb));
-        } else {
-            const double2 bb = ld2(vs.b + idx);
-            const double ra = DSUB(bb.x, ya), rb = DSUB(bb.y, yb);
-            st2(vs.R + idx, ra, rb); st2(vs.R0 + idx, ra, rb); st2(vs.P + idx, ra, rb);
-            a0 = DADD(a0, DMUL(bb.x, bb.x)); a1 = DADD(a1, DMUL(ra, ra));
-            a0 = DADD(a0, DMUL(bb.y, bb.y)); a1 = DADD(a1, DMUL(rb, rb));
-        }
-    } else {
-        if (wa) row_epilogue<MODE>(ya, idx, xa, vs, a0, a1);
-        if (wb) row_epilogue<MODE>(yb, idx + 1, xb, vs, a0, a1);
-    }
-}
-
+// Stores / accumulates the rows ya, yb of the cells at idx, idx+1 (wa / wb: row exists).  aux is
+// r0 (MODE_AP) or b (MODE_INIT) at idx; xa, xb the SpMV input at idx (MODE_AS).  Same arithmetic
+// and accumulation order as row_epilogue for cell a, then cell b.
 template <int MODE>
 __device__ __forceinline__ void pair_epilogue_pre(double ya, double yb, bool wa, bool wb, long long idx, double xa,
-                                                  double xb, double2 aux /* r0 (AP) or b (INIT) at idx */,
-                                                  const VecSet &vs, double &a0, double &a1)
+                                                  double xb, double2 aux, const VecSet &vs, double &a0, double &a1)
 {
-    // same arithmetic and accumulation order as row_epilogue for cell a then cell b
     if (MODE == MODE_INIT) {
         const double ra = DSUB(aux.x, ya), rb = DSUB(aux.y, yb);
         if (wa && wb) { st2(vs.R + idx, ra, rb); st2(vs.R0 + idx, ra, rb); st2(vs.P + idx, ra, rb); }
@@ -314,361 +279,19 @@ __device__ __forceinline__ void pair_epilogue_pre(double ya, double yb, bool wa,
     }
 }
 
-template <int MODE, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-k_stencil2_spmv(const SlabGeom G, const Coef cf, const MatCoef mc, const unsigned char *__restrict__ cls,
-                const int *__restrict__ geo, const VecSet vs, const IterCtl ctl, const int zc, double *partials,
-                const int pstride, const unsigned expected, const int finalize_here)
-{
-    __shared__ double sh[32];
-    if (!spmv_guard<MODE>(ctl)) return;
-    const int i0 = (blockIdx.x * 32 + threadIdx.x) * 2, j = blockIdx.y * 8 + threadIdx.y;
-    const int kb = G.k0 + blockIdx.z * zc;
-    const int ke = min(kb + zc, G.k1);
-    double a0 = 0.0, a1 = 0.0;
-    if (i0 < G.sdx && j < G.sdy) {
-        const int sdx = G.sdx, kdz = G.kdz, sdz = G.sdz;
-        const long long col = (long long)j * sdx + i0;
-        const bool xlA = (i0 == 0), xhB = (i0 + 2 == sdx), yl = (j == 0), yh = (j == G.sdy - 1);
-        const double cxpA = xlA ? cf.blo[0] : cf.msx;       // on cell a's right neighbour (= cell b)
-        const double cxmB = xhB ? cf.bhi[0] : cf.msx;       // on cell b's left neighbour (= cell a)
-        const double cym = yh ? cf.bhi[1] : cf.msy, cyp = yl ? cf.blo[1] : cf.msy;
-        const int by = (int)(yl | yh) << 1;
-        const double *__restrict__ xv = vs.x;
-        const long long ub = G.offU - (long long)G.gbase;    // U value of geoPHYS_C id g is xv[ub + g]
-        long long p = (long long)(kb - G.k0 + 1) * kdz + col;
-        double2 m[3], c[3], z1[3], z2[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const double *X = xv + q * G.segA + p;
-            c[q] = ld2(X);
-            m[q] = (kb > 0) ? ld2(X - kdz) : make_double2(0.0, 0.0);
-            z1[q] = (kb + 1 < sdz) ? ld2(X + kdz) : make_double2(0.0, 0.0);
-        }
-        for (int k = kb; k < ke; ++k, p += kdz) {
-            const bool zl = (k == 0), zh = (k == sdz - 1);
-            const bool pf = (k + 1 < ke) && (k + 2 < sdz);
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-                z2[q] = pf ? ld2(xv + q * G.segA + p + 2 * (long long)kdz) : make_double2(0.0, 0.0);
-            const uchar2 cl = *reinterpret_cast<const uchar2 *>(cls + (long long)(k - G.k0) * kdz + col);
-            const double czm = zh ? cf.bhi[2] : cf.msz, czp = zl ? cf.blo[2] : cf.msz;
-            const int bz = (int)(zl | zh) << 2;
-            const int bmA = (int)xlA | by | bz, bmB = (int)xhB | by | bz;
-            const double dgA = bmA ? cf.diag_b[bmA] : cf.diag_int, dgB = bmB ? cf.diag_b[bmB] : cf.diag_int;
-            const bool fA = (cl.x == 1), fB = (cl.y == 1);
-            const bool wA = (cl.x != 2), wB = (cl.y != 2);
-            // U gathers of the interior-conductor path (whenever one cell of the pair is interior
-            // conductor the other is a conductor cell too, numbered consecutively along x)
-            int gA = 0;
-            double uxm = 0.0, uA = 0.0, uB = 0.0, uxp = 0.0;
-            double2 uym = make_double2(0.0, 0.0), uyp = uym, uzm = uym, uzp = uym;
-            if (fA | fB) {
-                const int *gp = geo + (long long)(k - G.k0 + 2) * kdz + col;
-                gA = gp[0];
-                const int2 gjm = *reinterpret_cast<const int2 *>(gp - sdx), gjp = *reinterpret_cast<const int2 *>(gp + sdx);
-                const int2 gkm = *reinterpret_cast<const int2 *>(gp - kdz), gkp = *reinterpret_cast<const int2 *>(gp + kdz);
-                uA = xv[ub + gA]; uB = xv[ub + gA + 1];
-                if (fA) { uxm = xv[ub + gA - 1]; uym.x = xv[ub + gjm.x]; uyp.x = xv[ub + gjp.x]; uzm.x = xv[ub + gkm.x]; uzp.x = xv[ub + gkp.x]; }
-                if (fB) { uxp = xv[ub + gA + 2]; uym.y = xv[ub + gjm.y]; uyp.y = xv[ub + gjp.y]; uzm.y = xv[ub + gkm.y]; uzp.y = xv[ub + gkp.y]; }
-            }
-            double suA = 0.0, suB = 0.0;      // running A part of the U rows (ascending columns)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const double *X = xv + q * G.segA + p;
-                const double2 ym = yl ? make_double2(0.0, 0.0) : ld2(X - sdx);
-                const double2 yp = yh ? make_double2(0.0, 0.0) : ld2(X + sdx);
-                const double xm = xlA ? 0.0 : X[-1];
-                const double xp = xhB ? 0.0 : X[2];
-                double ya = 0.0, yb = 0.0;
-                if (fA) {
-                    ya = DADD(0.0, DMUL(mc.cm[2], m[q].x));
-                    ya = DADD(ya, DMUL(mc.cm[1], ym.x));
-                    ya = DADD(ya, DMUL(mc.cm[0], xm));
-                    ya = DADD(ya, DMUL(mc.diag, c[q].x));
-                    ya = DADD(ya, DMUL(mc.cp[0], c[q].y));
-                    ya = DADD(ya, DMUL(mc.cp[1], yp.x));
-                    ya = DADD(ya, DMUL(mc.cp[2], z1[q].x));
-                    const double um = (q == 0) ? uxm : (q == 1) ? uym.x : uzm.x;
-                    const double up = (q == 0) ? uB : (q == 1) ? uyp.x : uzp.x;
-                    ya = DADD(ya, DMUL(mc.g1[q], um));
-                    ya = DADD(ya, DMUL(-mc.g1[q], up));
-                    const double am = (q == 0) ? xm : (q == 1) ? ym.x : m[q].x;
-                    const double ap = (q == 0) ? c[q].y : (q == 1) ? yp.x : z1[q].x;
-                    suA = DADD(suA, DMUL(cf.ua_p[q], am));
-                    suA = DADD(suA, DMUL(cf.ua_m[q], ap));
-                } else if (wA) {
-                    if (!zl) ya = DADD(ya, DMUL(czm, m[q].x));
-                    if (!yl) ya = DADD(ya, DMUL(cym, ym.x));
-                    if (!xlA) ya = DADD(ya, DMUL(cf.msx, xm));
-                    ya = DADD(ya, DMUL(dgA, c[q].x));
-                    ya = DADD(ya, DMUL(cxpA, c[q].y));
-                    if (!yh) ya = DADD(ya, DMUL(cyp, yp.x));
-                    if (!zh) ya = DADD(ya, DMUL(czp, z1[q].x));
-                }
-                if (fB) {
-                    yb = DADD(0.0, DMUL(mc.cm[2], m[q].y));
-                    yb = DADD(yb, DMUL(mc.cm[1], ym.y));
-                    yb = DADD(yb, DMUL(mc.cm[0], c[q].x));
-                    yb = DADD(yb, DMUL(mc.diag, c[q].y));
-                    yb = DADD(yb, DMUL(mc.cp[0], xp));
-                    yb = DADD(yb, DMUL(mc.cp[1], yp.y));
-                    yb = DADD(yb, DMUL(mc.cp[2], z1[q].y));
-                    const double um = (q == 0) ? uA : (q == 1) ? uym.y : uzm.y;
-                    const double up = (q == 0) ? uxp : (q == 1) ? uyp.y : uzp.y;
-                    yb = DADD(yb, DMUL(mc.g1[q], um));
-                    yb = DADD(yb, DMUL(-mc.g1[q], up));
-                    const double am = (q == 0) ? c[q].x : (q == 1) ? ym.y : m[q].y;
-                    const double ap = (q == 0) ? xp : (q == 1) ? yp.y : z1[q].y;
-                    suB = DADD(suB, DMUL(cf.ua_p[q], am));
-                    suB = DADD(suB, DMUL(cf.ua_m[q], ap));
-                } else if (wB) {
-                    if (!zl) yb = DADD(yb, DMUL(czm, m[q].y));
-                    if (!yl) yb = DADD(yb, DMUL(cym, ym.y));
-                    yb = DADD(yb, DMUL(cxmB, c[q].x));
-                    yb = DADD(yb, DMUL(dgB, c[q].y));
-                    if (!xhB) yb = DADD(yb, DMUL(cf.msx, xp));
-                    if (!yh) yb = DADD(yb, DMUL(cyp, yp.y));
-                    if (!zh) yb = DADD(yb, DMUL(czp, z1[q].y));
-                }
-                pair_epilogue<MODE>(ya, yb, wA, wB, q * G.segA + p, c[q].x, c[q].y, vs, a0, a1);
-            }
-            if (fA) {       // U row of cell a: U columns k-1, j-1, i-1, centre, i+1, j+1, k+1
-                double s = suA;
-                s = DADD(s, DMUL(cf.msz, uzm.x)); s = DADD(s, DMUL(cf.msy, uym.x)); s = DADD(s, DMUL(cf.msx, uxm));
-                s = DADD(s, DMUL(cf.diag_int, uA));
-                s = DADD(s, DMUL(cf.msx, uB)); s = DADD(s, DMUL(cf.msy, uyp.x)); s = DADD(s, DMUL(cf.msz, uzp.x));
-                row_epilogue<MODE>(s, ub + gA, uA, vs, a0, a1);
-            }
-            if (fB) {
-                double s = suB;
-                s = DADD(s, DMUL(cf.msz, uzm.y)); s = DADD(s, DMUL(cf.msy, uym.y)); s = DADD(s, DMUL(cf.msx, uA));
-                s = DADD(s, DMUL(cf.diag_int, uB));
-                s = DADD(s, DMUL(cf.msx, uxp)); s = DADD(s, DMUL(cf.msy, uyp.y)); s = DADD(s, DMUL(cf.msz, uzp.y));
-                row_epilogue<MODE>(s, ub + gA + 1, uB, vs, a0, a1);
-            }
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { m[q] = c[q]; c[q] = z1[q]; z1[q] = z2[q]; }
-        }
-    }
-    if (MODE != MODE_PLAIN) {
-        const int pidx = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        const unsigned ex = finalize_here ? expected : 0xffffffffu;
-        if (MODE == MODE_AP)
-            reduce_epilogue<1>(a0, 0.0, partials, pstride, pidx, ex, ctl.sc, RED_APR0, RED_APR0, sh);
-        else if (MODE == MODE_AS)
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, ex, ctl.sc, RED_ASS, RED_ASAS, sh);
-        else
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, ex, ctl.sc, RED_BB, RED_RR_INIT, sh);
-    }
-}
-
-// --------------------------------------------------------------------------------------------
-// K2 (main path, v3): like k_stencil2_spmv but ONE vector component per thread (blockIdx.z =
-// 3*zchunk + comp), so a thread keeps only 4 double2 of marching state and ~64 registers: four
-// CTAs per SM, every thread with a 16-byte prefetch plus its neighbour loads in flight.  The three
-// A rows of a cell are independent of each other; the Az threads also compute the 13-entry U row
-// of interior conductor cells (Ax(i+-1), Ay(j+-1) come through L1/L2).
-// --------------------------------------------------------------------------------------------
-template <int MODE, int MINB, int DBG = 0>
-__global__ void __launch_bounds__(256, MINB)
-k_stencil3_spmv(const SlabGeom G, const Coef cf, const MatCoef mc, const unsigned char *__restrict__ cls,
-                const int *__restrict__ geo, const VecSet vs, const IterCtl ctl, const int zc, double *partials,
-                const int pstride, const unsigned expected, const int finalize_here)
-{
-    __shared__ double sh[32];
-    if (!spmv_guard<MODE>(ctl)) return;
-    const int comp = blockIdx.z % 3, zchunk = blockIdx.z / 3;
-    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2, j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int kb = G.k0 + zchunk * zc;
-    const int ke = min(kb + zc, G.k1);
-    double a0 = 0.0, a1 = 0.0;
-    if (i0 < G.sdx && j < G.sdy) {
-        const int sdx = G.sdx, kdz = G.kdz, sdz = G.sdz;
-        const long long col = (long long)j * sdx + i0;
-        const bool xlA = (i0 == 0), xhB = (i0 + 2 == sdx), yl = (j == 0), yh = (j == G.sdy - 1);
-        const double cxpA = xlA ? cf.blo[0] : cf.msx;
-        const double cxmB = xhB ? cf.bhi[0] : cf.msx;
-        const double cym = yh ? cf.bhi[1] : cf.msy, cyp = yl ? cf.blo[1] : cf.msy;
-        const int by = (int)(yl | yh) << 1;
-        const double *__restrict__ xv = vs.x;
-        const long long ub = G.offU - (long long)G.gbase;
-        const long long cb = (long long)comp * G.segA;                // this component's segment
-        long long p = (long long)(kb - G.k0 + 1) * kdz + col;
-        const double g1c = mc.g1[comp];
-        const double2 zero2 = make_double2(0.0, 0.0);
-        // marching state: planes k-1, k in m, c; planes k+1 .. k+PF in zq[]; plane k+PF+1 is issued at
-        // the top of iteration k, so PF 16-byte DRAM loads per thread are always in flight
-        constexpr int PF = 1;
-        double2 m, c, zq[PF];
-        const double *__restrict__ aux = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : nullptr;
-        double2 auxc = zero2;
-        {
-            const double *X = xv + cb + p;
-            c = ld2(X);
-            m = (kb > 0) ? ld2(X - kdz) : zero2;
-#pragma unroll
-            for (int d = 0; d < PF; ++d)
-                zq[d] = ((d == 0 || kb + d < ke) && (kb + d + 1 < sdz)) ? ld2(X + (long long)(d + 1) * kdz) : zero2;
-            if (MODE == MODE_AP || MODE == MODE_INIT) auxc = ld2(aux + cb + p);
-        }
-        for (int k = kb; k < ke; ++k, p += kdz) {
-            const bool zl = (k == 0), zh = (k == sdz - 1);
-            const double *X = xv + cb + p;
-            const double2 znew = ((k + PF < ke) && (k + PF + 1 < sdz)) ? ld2(X + (long long)(PF + 1) * kdz) : zero2;
-            double2 auxn = zero2;
-            if ((MODE == MODE_AP || MODE == MODE_INIT) && (k + 1 < ke)) auxn = ld2(aux + cb + p + kdz);
-            const double2 z1 = zq[0];
-            const uchar2 cl = *reinterpret_cast<const uchar2 *>(cls + (long long)(k - G.k0) * kdz + col);
-            const double2 ym = (DBG & 1) ? m : yl ? make_double2(0.0, 0.0) : ld2(X - sdx);
-            const double2 yp = (DBG & 1) ? z1 : yh ? make_double2(0.0, 0.0) : ld2(X + sdx);
-            const double xm = (DBG & 1) ? c.y : xlA ? 0.0 : X[-1];
-            const double xp = (DBG & 1) ? c.x : xhB ? 0.0 : X[2];
-            const bool fA = (DBG & 4) ? false : (cl.x == 1), fB = (DBG & 4) ? false : (cl.y == 1);
-            const bool wA = (DBG & 2) ? (cl.x == 77) : (cl.x != 2), wB = (DBG & 2) ? (cl.y == 77) : (cl.y != 2);
-            double ya = 0.0, yb = 0.0;
-            if (DBG & 2) { a0 = DADD(a0, DADD(DADD(m.x, c.y), DADD(z1.x, ym.y))); a1 = DADD(a1, DADD(DADD(yp.x, xm), xp)); }
-            if (fA | fB) {
-                // interior conductor: both cells of the pair are conductor cells, numbered
-                // consecutively along x.  Gather the U values this component's rows need.
-                const int *gp = geo + (long long)(k - G.k0 + 2) * kdz + col;
-                const int gA = gp[0];
-                double umA = 0.0, upA = 0.0, umB = 0.0, upB = 0.0;   // U(-1), U(+1) along this axis
-                if (comp == 0) {
-                    const double uA = xv[ub + gA], uB = xv[ub + gA + 1];
-                    umB = uA; upA = uB;
-                    if (fA) umA = xv[ub + gA - 1];
-                    if (fB) upB = xv[ub + gA + 2];
-                } else {
-                    const int st = (comp == 1) ? sdx : kdz;
-                    const int2 gm = *reinterpret_cast<const int2 *>(gp - st), gq = *reinterpret_cast<const int2 *>(gp + st);
-                    if (fA) { umA = xv[ub + gm.x]; upA = xv[ub + gq.x]; }
-                    if (fB) { umB = xv[ub + gm.y]; upB = xv[ub + gq.y]; }
-                }
-                if (fA) {
-                    ya = DADD(0.0, DMUL(mc.cm[2], m.x));
-                    ya = DADD(ya, DMUL(mc.cm[1], ym.x));
-                    ya = DADD(ya, DMUL(mc.cm[0], xm));
-                    ya = DADD(ya, DMUL(mc.diag, c.x));
-                    ya = DADD(ya, DMUL(mc.cp[0], c.y));
-                    ya = DADD(ya, DMUL(mc.cp[1], yp.x));
-                    ya = DADD(ya, DMUL(mc.cp[2], z1.x));
-                    ya = DADD(ya, DMUL(g1c, umA));
-                    ya = DADD(ya, DMUL(-g1c, upA));
-                }
-                if (fB) {
-                    yb = DADD(0.0, DMUL(mc.cm[2], m.y));
-                    yb = DADD(yb, DMUL(mc.cm[1], ym.y));
-                    yb = DADD(yb, DMUL(mc.cm[0], c.x));
-                    yb = DADD(yb, DMUL(mc.diag, c.y));
-                    yb = DADD(yb, DMUL(mc.cp[0], xp));
-                    yb = DADD(yb, DMUL(mc.cp[1], yp.y));
-                    yb = DADD(yb, DMUL(mc.cp[2], z1.y));
-                    yb = DADD(yb, DMUL(g1c, umB));
-                    yb = DADD(yb, DMUL(-g1c, upB));
-                }
-                if (comp == 2) {
-                    // U rows (EC3D.f90:917-922): A columns Ax(i-1),Ax(i+1),Ay(j-1),Ay(j+1),Az(k-1),Az(k+1),
-                    // then U columns k-1, j-1, i-1, centre, i+1, j+1, k+1.  umA/upA hold U(k-1)/U(k+1).
-                    const double *X0 = xv + p, *X1 = xv + G.segA + p;
-                    const double2 a0c = ld2(X0);
-                    const double2 a1m = ld2(X1 - sdx), a1p = ld2(X1 + sdx);
-                    const int2 gjm = *reinterpret_cast<const int2 *>(gp - sdx), gjp = *reinterpret_cast<const int2 *>(gp + sdx);
-                    const double uA = xv[ub + gA], uB = xv[ub + gA + 1];
-                    if (fA) {
-                        double s = DADD(0.0, DMUL(cf.ua_p[0], X0[-1]));
-                        s = DADD(s, DMUL(cf.ua_m[0], a0c.y));
-                        s = DADD(s, DMUL(cf.ua_p[1], a1m.x));
-                        s = DADD(s, DMUL(cf.ua_m[1], a1p.x));
-                        s = DADD(s, DMUL(cf.ua_p[2], m.x));
-                        s = DADD(s, DMUL(cf.ua_m[2], z1.x));
-                        s = DADD(s, DMUL(cf.msz, umA));
-                        s = DADD(s, DMUL(cf.msy, xv[ub + gjm.x]));
-                        s = DADD(s, DMUL(cf.msx, xv[ub + gA - 1]));
-                        s = DADD(s, DMUL(cf.diag_int, uA));
-                        s = DADD(s, DMUL(cf.msx, uB));
-                        s = DADD(s, DMUL(cf.msy, xv[ub + gjp.x]));
-                        s = DADD(s, DMUL(cf.msz, upA));
-                        row_epilogue<MODE>(s, ub + gA, uA, vs, a0, a1);
-                    }
-                    if (fB) {
-                        double s = DADD(0.0, DMUL(cf.ua_p[0], a0c.x));
-                        s = DADD(s, DMUL(cf.ua_m[0], X0[2]));
-                        s = DADD(s, DMUL(cf.ua_p[1], a1m.y));
-                        s = DADD(s, DMUL(cf.ua_m[1], a1p.y));
-                        s = DADD(s, DMUL(cf.ua_p[2], m.y));
-                        s = DADD(s, DMUL(cf.ua_m[2], z1.y));
-                        s = DADD(s, DMUL(cf.msz, umB));
-                        s = DADD(s, DMUL(cf.msy, xv[ub + gjm.y]));
-                        s = DADD(s, DMUL(cf.msx, uA));
-                        s = DADD(s, DMUL(cf.diag_int, uB));
-                        s = DADD(s, DMUL(cf.msx, xv[ub + gA + 2]));
-                        s = DADD(s, DMUL(cf.msy, xv[ub + gjp.y]));
-                        s = DADD(s, DMUL(cf.msz, upB));
-                        row_epilogue<MODE>(s, ub + gA + 1, uB, vs, a0, a1);
-                    }
-                }
-            }
-            if (!fA | !fB) {
-                const double czm = zh ? cf.bhi[2] : cf.msz, czp = zl ? cf.blo[2] : cf.msz;
-                const int bz = (int)(zl | zh) << 2;
-                if (!fA && wA) {
-                    const int bm = (int)xlA | by | bz;
-                    const double dg = bm ? cf.diag_b[bm] : cf.diag_int;
-                    if (!zl) ya = DADD(ya, DMUL(czm, m.x));
-                    if (!yl) ya = DADD(ya, DMUL(cym, ym.x));
-                    if (!xlA) ya = DADD(ya, DMUL(cf.msx, xm));
-                    ya = DADD(ya, DMUL(dg, c.x));
-                    ya = DADD(ya, DMUL(cxpA, c.y));
-                    if (!yh) ya = DADD(ya, DMUL(cyp, yp.x));
-                    if (!zh) ya = DADD(ya, DMUL(czp, z1.x));
-                }
-                if (!fB && wB) {
-                    const int bm = (int)xhB | by | bz;
-                    const double dg = bm ? cf.diag_b[bm] : cf.diag_int;
-                    if (!zl) yb = DADD(yb, DMUL(czm, m.y));
-                    if (!yl) yb = DADD(yb, DMUL(cym, ym.y));
-                    yb = DADD(yb, DMUL(cxmB, c.x));
-                    yb = DADD(yb, DMUL(dg, c.y));
-                    if (!xhB) yb = DADD(yb, DMUL(cf.msx, xp));
-                    if (!yh) yb = DADD(yb, DMUL(cyp, yp.y));
-                    if (!zh) yb = DADD(yb, DMUL(czp, z1.y));
-                }
-            }
-            pair_epilogue_pre<MODE>(ya, yb, wA, wB, cb + p, c.x, c.y, auxc, vs, a0, a1);
-            m = c; c = z1;
-#pragma unroll
-            for (int d = 0; d + 1 < PF; ++d) zq[d] = zq[d + 1];
-            zq[PF - 1] = znew;
-            auxc = auxn;
-        }
-    }
-    if (MODE != MODE_PLAIN) {
-        const int pidx = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        const unsigned ex = finalize_here ? expected : 0xffffffffu;
-        if (MODE == MODE_AP)
-            reduce_epilogue<1>(a0, 0.0, partials, pstride, pidx, ex, ctl.sc, RED_APR0, RED_APR0, sh);
-        else if (MODE == MODE_AS)
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, ex, ctl.sc, RED_ASS, RED_ASAS, sh);
-        else
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, ex, ctl.sc, RED_BB, RED_RR_INIT, sh);
-    }
-}
-
 // --------------------------------------------------------------------------------------------
 // K2b: matrix-free SpMV, conductor cells: three A rows with convection, 2C/dt and grad-U coupling
 // (EC3D.f90:656-710) plus the U row (EC3D.f90:766-922).  One thread per owned conductor cell.
 // --------------------------------------------------------------------------------------------
-struct GatherVisitor {
+struct GatherVisitor {      // used with a dense GeoView: U column g = 1 + offset in the dense U box
     const double *__restrict__ x;
     long long segA, offU, cell_shift;   // local A index = comp*segA + cell0 - cell_shift
-    int gbase;
     double s;
     __device__ __forceinline__ void a(int comp, long long cell0, double coef)
     {
         s = DADD(s, DMUL(coef, x[comp * segA + (cell0 - cell_shift)]));
     }
-    __device__ __forceinline__ void u(int g, double coef) { s = DADD(s, DMUL(coef, x[offU + (g - gbase)])); }
+    __device__ __forceinline__ void u(int g, double coef) { s = DADD(s, DMUL(coef, x[offU + (g - 1)])); }
 };
 
 template <int MODE>
@@ -685,12 +308,12 @@ k_cond_spmv(const SlabGeom G, const Coef cf, const MatCoef *__restrict__ mcs, co
     if (t < ncond) {
         const int cell0 = cond_cells[t];
         const int k = cell0 / G.kdz, rem = cell0 - k * G.kdz, j = rem / G.sdx, i = rem - j * G.sdx;
-        GeoView gv{geo, G.sdx, G.sdy, G.kdz, G.k0 - 2, G.nzl + 4};
+        const GeoView gv = dense_view(G, geo);
         const long long cell_shift = (long long)(G.k0 - 1) * G.kdz;
         const long long lp = (long long)cell0 - cell_shift;
         const long long lmat = (long long)cell0 - (long long)(G.k0 - 2) * G.kdz;
         const MatCoef mc = mcs[mat[lmat] - 1];
-        GatherVisitor v{vs.x, G.segA, G.offU, cell_shift, G.gbase, 0.0};
+        GatherVisitor v{vs.x, G.segA, G.offU, cell_shift, 0.0};
 #pragma unroll
         for (int comp = 0; comp < 3; ++comp) {
             v.s = 0.0;
@@ -699,7 +322,7 @@ k_cond_spmv(const SlabGeom G, const Coef cf, const MatCoef *__restrict__ mcs, co
         }
         v.s = 0.0;
         cond_u_row(cf, gv, i, j, k, 3, v);
-        const long long lu = G.offU + (gv.at(i, j, k) - G.gbase);
+        const long long lu = u_local(G, i, j, k);
         row_epilogue<MODE>(v.s, lu, vs.x[lu], vs, a0, a1);
     }
     if (MODE != MODE_PLAIN) {

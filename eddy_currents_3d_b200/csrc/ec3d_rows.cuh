@@ -9,21 +9,34 @@
 // Visitor concept:
 //   void a(int comp, long long cell0, double coef);   // A column: component comp, 0-based GLOBAL cell
 //   void u(int g, double coef);                       // U column: geoPHYS_C value g (3*nC + m); g <= 0 is invalid
+//                                                     // (with a dense GeoView: 1 + index into the dense U box)
 // Entries are visited in ascending column order (the order full_sort produces, utilites.f90:477).
 #pragma once
 #include "ec3d_common.cuh"
 
 // Local view of geoPHYS_C around a slab: planes [gz0, gz0+gnz), zero outside.
+// With dense != 0 a conductor cell is reported as 1 + its offset inside the dense U box of the local
+// vector layout (SlabGeom::ub_*), which is what the gathering visitors of the SpMV / RHS kernels
+// index with; the assembly kernels use the plain view (real geoPHYS_C values = CSR columns).
 struct GeoView {
     const int *g;
     int sdx, sdy, kdz;
     int gz0, gnz;
+    int dense, ub_i0, ub_j0, ub_kl0, ub_nx;
+    long long ub_pl;
     __host__ __device__ __forceinline__ int at(int i, int j, int k) const {
         int kk = k - gz0;
         if (i < 0 || i >= sdx || j < 0 || j >= sdy || kk < 0 || kk >= gnz) return 0;
-        return g[(long long)kk * kdz + (long long)j * sdx + i];
+        const int v = g[(long long)kk * kdz + (long long)j * sdx + i];
+        if (!dense || v == 0) return v;
+        return 1 + (int)((long long)(k - ub_kl0) * ub_pl + (long long)(j - ub_j0) * ub_nx + (i - ub_i0));
     }
 };
+
+__host__ __device__ __forceinline__ GeoView dense_view(const SlabGeom &G, const int *geo)
+{
+    return GeoView{geo, G.sdx, G.sdy, G.kdz, G.k0 - 2, G.nzl + 4, 1, G.ub_i0, G.ub_j0, G.ub_kl0, G.ub_nx, G.ub_pl};
+}
 
 // ---- A row of a non-conductor cell or of any cell on a domain face (EC3D.f90:528-654) ----
 // Domain-face cells ignore conductor properties (no kFi branch there).

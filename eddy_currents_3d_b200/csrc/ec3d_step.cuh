@@ -130,7 +130,7 @@ k_rhs_pre(const SlabGeom G, const Coef cf, const int *__restrict__ geo, const in
     if (t >= ncond) return;
     const int cell0 = cond_cells[t];
     const int k = cell0 / G.kdz, rem = cell0 - k * G.kdz, j = rem / G.sdx, i = rem - j * G.sdx;
-    GeoView gv{geo, G.sdx, G.sdy, G.kdz, G.k0 - 2, G.nzl + 4};
+    const GeoView gv = dense_view(G, geo);
     const long long cell_shift = (long long)(G.k0 - 1) * G.kdz;
     const long long lp = (long long)cell0 - cell_shift;
     const int f = flags[t];
@@ -141,9 +141,9 @@ k_rhs_pre(const SlabGeom G, const Coef cf, const int *__restrict__ geo, const in
         Jaf[idx] = ((f >> comp) & 1) ? 0.0 : DADD(DMUL(valdom, Uaf[idx]), Jaf[idx]);
     }
     // U row: sum over the A columns of the row (:385-392), zero on cel_bndUx/Uy/Uz (:396-398)
-    GatherVisitor v{Uaf, G.segA, G.offU, cell_shift, G.gbase, 0.0};
+    GatherVisitor v{Uaf, G.segA, G.offU, cell_shift, 0.0};
     cond_u_row(cf, gv, i, j, k, 1, v);
-    const long long lu = G.offU + (gv.at(i, j, k) - G.gbase);
+    const long long lu = u_local(G, i, j, k);
     Jaf[lu] = ((f >> 3) & 7) ? 0.0 : v.s;
 }
 

@@ -1,0 +1,477 @@
+// ec3d_tma.cuh -- K2 (main path): TMA-staged matrix-free SpMV of the coupled A-U operator, sm_100a.
+//
+// Why TMA: a register-marching stencil is latency bound -- every plane needs fresh cache lines and a
+// thread keeps only one or two 16-byte loads in flight (ncu on the first version: long-scoreboard
+// stalls, 24 % warps active, DRAM at 30 %).  Here ONE elected thread per CTA posts
+// `cp.async.bulk.tensor` copies of whole (x,y) tiles -- with their halo, zero-filled outside the
+// domain by the hardware -- into a ring of shared-memory stages several planes ahead; each stage is
+// guarded by an mbarrier that the copy engine completes (complete_tx).  The 256 compute threads only
+// touch shared memory and registers, so the bytes in flight per SM are set by the ring depth
+// (NSTAGE-2 stages x 16-22 KB x 2 CTAs), not by registers.
+//
+// One CTA = a 64 x 8 (x,y) tile, all three vector components and the U block, marching over `zc`
+// planes; each thread owns two x-adjacent cells (16-byte shared loads / global stores) and keeps the
+// k-1 / k / k+1 values of Ax, Ay, Az and U of its pair in registers.  Per plane the ring delivers
+//     xs : 68 x 10 doubles x 3 components  (one 4-D TMA box of the input vector's A part)
+//     us : 68 x 10 doubles                 (3-D TMA box of the dense U box; only for tiles that
+//                                           touch the conductor's bounding box)
+//     cs : 64 x 8 class bytes              (3-D TMA box of the class map)
+// and every row of every cell of the tile is produced in that one pass:
+//     * A rows of air / domain-face cells ........ EC3D.f90:528-654
+//     * A rows of conductor cells ................ EC3D.f90:656-710 (convection, 2C/dt, grad U:
+//                                                  central or one-sided, chosen by the class byte)
+//     * U rows of conductor cells ................ EC3D.f90:766-922 (interior 13-entry rows and the
+//                                                  26 corner / edge / face cases incl. the :803-807
+//                                                  sign anomaly)
+// The per-cell class byte (k_build_cls2) is 0 for non-conductor cells, else 0x40 | sx | sy<<2 | sz<<4
+// with s_axis bit0 = '-' neighbour is not a conductor, bit1 = '+' neighbour is not: everything the
+// row rules branch on, so geoPHYS_C is not read here at all.  One-sided gradients reach two cells:
+// U(i+-2) is inside the tile (2 halo columns), U(j+-2) and U(k+-2) are read straight from the dense U
+// box (only surface cells do that).
+// Rows are summed in ascending column order with unfused mul/add starting from 0.0, i.e. exactly the
+// sequential CSR row sum of the reference's sprsAx (solvers.f90:54-61) on the assembled matrix.
+// The dot products of BiCGSTABwr that follow the SpMV are fused in (MODE_AP / MODE_AS / MODE_INIT).
+#pragma once
+#include <cuda.h>
+
+#include "ec3d_kernels.cuh"
+
+namespace tma {
+
+constexpr int TX = 64, TY = 8;              // cells per plane tile (2 cells per thread, 256 threads)
+constexpr int BW = TX + 4, BH = TY + 2;     // halo box: 2 extra columns each side keep the own pair 16-byte aligned
+constexpr int TILE_D = BW * BH;             // 680 doubles
+constexpr int TILE_BYTES = TILE_D * 8;      // 5440
+constexpr int XS_BYTES = 3 * TILE_BYTES;    // 16320: one TMA box 68 x 10 x 1 x 3
+constexpr int CLS_OFF = 16384;              // class-byte tile (64 x 8 bytes) inside a stage (128-byte aligned)
+constexpr int CLS_BYTES = TX * TY;          // 512
+constexpr int US_OFF = CLS_OFF + CLS_BYTES; // 16896 = 132 * 128: U tile
+constexpr int STAGE_BYTES = US_OFF + 5504;  // 22400 = 175 * 128
+constexpr int smem_bytes(int nstage) { return nstage * STAGE_BYTES + 128; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+__device__ __forceinline__ void load4d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+__device__ __forceinline__ void load3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// TMA prefetch of a tile into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void prefetch4d(const CUtensorMap *map, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void prefetch3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// U values of one cell along one axis at offsets -2 .. +2
+struct U5 {
+    double m2, m1, c0, p1, p2;
+};
+
+// A row (component / axis AX) of a conductor cell: 7 A columns (EC3D.f90:649-663) then the grad-U
+// columns (:667-710) -- backward one-sided when the '+' neighbour is missing, forward one-sided when
+// only the '-' neighbour is, central otherwise.  sa = that axis' 2-bit state.
+template <int AX>
+__device__ __forceinline__ double cond_a(const MatCoef &mc, const int sa, const double zm, const double ym, const double xm,
+                                         const double cc, const double xp, const double yp, const double zp, const U5 &u)
+{
+    double y = DADD(0.0, DMUL(mc.cm[2], zm));
+    y = DADD(y, DMUL(mc.cm[1], ym));
+    y = DADD(y, DMUL(mc.cm[0], xm));
+    y = DADD(y, DMUL(mc.diag, cc));
+    y = DADD(y, DMUL(mc.cp[0], xp));
+    y = DADD(y, DMUL(mc.cp[1], yp));
+    y = DADD(y, DMUL(mc.cp[2], zp));
+    if (sa & 2) {
+        y = DADD(y, DMUL(-mc.g1[AX], u.m2));
+        y = DADD(y, DMUL(mc.g4[AX], u.m1));
+        y = DADD(y, DMUL(-mc.g3[AX], u.c0));
+    } else if (sa & 1) {
+        y = DADD(y, DMUL(mc.g3[AX], u.c0));
+        y = DADD(y, DMUL(-mc.g4[AX], u.p1));
+        y = DADD(y, DMUL(mc.g1[AX], u.p2));
+    } else {
+        y = DADD(y, DMUL(mc.g1[AX], u.m1));
+        y = DADD(y, DMUL(-mc.g1[AX], u.p1));
+    }
+    return y;
+}
+
+// A-column part of a U row, contribution of component AX, added to the running sum in ascending
+// column order (interior: A(-1), A(+1) of that axis, EC3D.f90:917-922; surface: the same cell's A
+// with -+2/(dt*d), only for axes with a missing neighbour, :773-916, anomaly at :803-807).
+template <int AX>
+__device__ __forceinline__ double urow_a(const Coef &cf, const int st, const double am, const double ac, const double ap,
+                                         double s)
+{
+    const int sx = st & 3, sy = (st >> 2) & 3, sz = (st >> 4) & 3;
+    if ((st & 63) == 0) {
+        s = DADD(s, DMUL(cf.ua_p[AX], am));
+        s = DADD(s, DMUL(cf.ua_m[AX], ap));
+        return s;
+    }
+    const bool anomaly = (sx == 1 && sy == 2 && sz == 2);
+    const int sa = (AX == 0) ? sx : (AX == 1) ? sy : sz;
+    if (sa) {
+        double coef = (sa == 1) ? cf.uc_m[AX] : cf.uc_p[AX];
+        if (anomaly && AX == 0) coef = cf.uc_p[0];
+        if (anomaly && AX == 1) coef = cf.uc_m[1];
+        s = DADD(s, DMUL(coef, ac));
+    }
+    return s;
+}
+
+// U-column part of a U row: k-1, j-1, i-1, centre, i+1, j+1, k+1 (ascending U numbers).
+__device__ __forceinline__ double urow_u(const Coef &cf, const int st, const double ukm, const double ujm, const double uim,
+                                         const double uc, const double uip, const double ujp, const double ukp, double s)
+{
+    const int sx = st & 3, sy = (st >> 2) & 3, sz = (st >> 4) & 3;
+    if (sz == 0) s = DADD(s, DMUL(cf.msz, ukm)); else if (sz == 2) s = DADD(s, DMUL(cf.m2s[2], ukm));
+    if (sy == 0) s = DADD(s, DMUL(cf.msy, ujm)); else if (sy == 2) s = DADD(s, DMUL(cf.m2s[1], ujm));
+    if (sx == 0) s = DADD(s, DMUL(cf.msx, uim)); else if (sx == 2) s = DADD(s, DMUL(cf.m2s[0], uim));
+    s = DADD(s, DMUL(cf.diag_int, uc));
+    if (sx == 0) s = DADD(s, DMUL(cf.msx, uip)); else if (sx == 1) s = DADD(s, DMUL(cf.m2s[0], uip));
+    if (sy == 0) s = DADD(s, DMUL(cf.msy, ujp)); else if (sy == 1) s = DADD(s, DMUL(cf.m2s[1], ujp));
+    if (sz == 0) s = DADD(s, DMUL(cf.msz, ukp)); else if (sz == 1) s = DADD(s, DMUL(cf.m2s[2], ukp));
+    return s;
+}
+
+}  // namespace tma
+
+// Class byte of the TMA SpMV for every owned cell (layout [k-k0][j][i], row pitch clsx = sdx rounded
+// up to 16 so the map is a legal TMA tensor).
+__global__ void k_build_cls2(const SlabGeom G, const int *__restrict__ geo, const int *__restrict__ cond_cells,
+                             const int ncond, unsigned char *__restrict__ cls, const int clsx)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncond) return;
+    const int cell0 = cond_cells[t];
+    const int k = cell0 / G.kdz, rem = cell0 - k * G.kdz, j = rem / G.sdx, i = rem - j * G.sdx;
+    GeoView gv{geo, G.sdx, G.sdy, G.kdz, G.k0 - 2, G.nzl + 4};
+    const int sx = (gv.at(i - 1, j, k) == 0) | ((gv.at(i + 1, j, k) == 0) << 1);
+    const int sy = (gv.at(i, j - 1, k) == 0) | ((gv.at(i, j + 1, k) == 0) << 1);
+    const int sz = (gv.at(i, j, k - 1) == 0) | ((gv.at(i, j, k + 1) == 0) << 1);
+    cls[((long long)(k - G.k0) * G.sdy + j) * clsx + i] = (unsigned char)(0x40 | sx | (sy << 2) | (sz << 4));
+}
+
+// Row epilogue of a cell pair: stores, and the fused BiCGSTABwr dot products.  The products of the
+// dots are accumulated with fma (the reference's sequential dot_product order is not reproducible
+// in parallel anyway; fewer roundings, half the FP64 instructions).
+template <int MODE>
+__device__ __forceinline__ void pair_out(const double ya, const double yb, const bool wa, const bool wb, const long long idx,
+                                         const double xa, const double xb, const double2 aux, const VecSet &vs,
+                                         double &a0, double &a1)
+{
+    if (MODE == MODE_INIT) {
+        const double ra = DSUB(aux.x, ya), rb = DSUB(aux.y, yb);
+        if (wa && wb) { st2(vs.R + idx, ra, rb); st2(vs.R0 + idx, ra, rb); st2(vs.P + idx, ra, rb); }
+        else {
+            if (wa) { vs.R[idx] = ra; vs.R0[idx] = ra; vs.P[idx] = ra; }
+            if (wb) { vs.R[idx + 1] = rb; vs.R0[idx + 1] = rb; vs.P[idx + 1] = rb; }
+        }
+        if (wa) { a0 = __fma_rn(aux.x, aux.x, a0); a1 = __fma_rn(ra, ra, a1); }
+        if (wb) { a0 = __fma_rn(aux.y, aux.y, a0); a1 = __fma_rn(rb, rb, a1); }
+        return;
+    }
+    if (wa && wb) st2(vs.y + idx, ya, yb);
+    else {
+        if (wa) vs.y[idx] = ya;
+        if (wb) vs.y[idx + 1] = yb;
+    }
+    if (MODE == MODE_AP) {
+        if (wa) a0 = __fma_rn(ya, aux.x, a0);
+        if (wb) a0 = __fma_rn(yb, aux.y, a0);
+    } else if (MODE == MODE_AS) {
+        if (wa) { a0 = __fma_rn(ya, xa, a0); a1 = __fma_rn(ya, ya, a1); }
+        if (wb) { a0 = __fma_rn(yb, xb, a0); a1 = __fma_rn(yb, yb, a1); }
+    }
+}
+
+// 7-point row with per-position coefficients.  Neighbours that do not exist (domain faces) arrive
+// as +0.0 from the TMA zero fill / the zero halo planes, and coef * 0 = +-0 added to a partial sum
+// that is never -0.0 (it starts from +0.0) leaves every bit unchanged -- so the row equals the
+// reference's shorter boundary row (EC3D.f90:528-646) without a single branch.
+__device__ __forceinline__ double row7(const double czm, const double cym, const double cxm, const double dg, const double cxp,
+                                       const double cyp, const double czp, const double zm, const double ym,
+                                       const double xm, const double cc, const double xp, const double yp,
+                                       const double zp)
+{
+    double y = __fma_rn(czm, zm, 0.0);          // == 0.0 + czm*zm, one rounding either way
+    y = DADD(y, DMUL(cym, ym));
+    y = DADD(y, DMUL(cxm, xm));
+    y = DADD(y, DMUL(dg, cc));
+    y = DADD(y, DMUL(cxp, xp));
+    y = DADD(y, DMUL(cyp, yp));
+    y = DADD(y, DMUL(czp, zp));
+    return y;
+}
+
+template <int MODE, int NSTAGE>
+__global__ void __launch_bounds__(256, 2)
+k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmU,
+           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAuxA,
+           const __grid_constant__ CUtensorMap tmAuxU, const SlabGeom G, const Coef cf, const MatCoef mc,
+           const VecSet vs, const IterCtl ctl, const int zc, double *partials, const int pstride,
+           const unsigned expected, const int finalize_here)
+{
+    using namespace tma;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ double sh[32];
+    __shared__ __align__(8) unsigned long long full[NSTAGE];
+    if (!spmv_guard<MODE>(ctl)) return;
+    unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = tx + 32 * ty;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int kb = G.k0 + blockIdx.z * zc;
+    const int ke = min(kb + zc, G.k1);
+    const int nload = (ke - kb) + 2;                        // planes kb-1 .. ke
+    constexpr bool HAS_AUX = (MODE == MODE_AP || MODE == MODE_INIT);
+    // does this tile column touch the conductor's bounding box?
+    const bool tileU = (G.ub_nz > 0) && (x0 < G.ub_i0 + G.ub_nx) && (x0 + TX > G.ub_i0) && (y0 < G.ub_j0 + G.ub_ny) &&
+                       (y0 + TY > G.ub_j0);
+    const int ukA = G.ub_k0 - 1, ukB = G.ub_k0 + G.ub_nz;  // U tiles are needed for planes [ukA, ukB]
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(full + s, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    auto issue = [&](int q) {                               // q-th plane of this chunk: pl = kb-1+q
+        const int pl = kb - 1 + q, s = q % NSTAGE;
+        unsigned char *st = smem + s * STAGE_BYTES;
+        const bool u_ = tileU && pl >= ukA && pl <= ukB;
+        const bool c_ = pl >= kb && pl < ke;                // class bytes only for planes that are computed
+        mbar_expect_tx(full + s, XS_BYTES + (u_ ? TILE_BYTES : 0) + (c_ ? CLS_BYTES : 0));
+        load4d(st, &tmX, full + s, x0 - 2, y0 - 1, pl - G.k0 + 1, 0);
+        if (u_) load3d(st + US_OFF, &tmU, full + s, x0 - 2 - G.ub_i0, y0 - 1 - G.ub_j0, pl - G.ub_kl0);
+        if (c_) load3d(st + CLS_OFF, &tmC, full + s, x0, y0, pl - G.k0);
+        if (HAS_AUX && c_) {                                // r0 / b of that plane: pull into L2 ahead of the LDGs
+            prefetch4d(&tmAuxA, x0 - 2, y0 - 1, pl - G.k0 + 1, 0);
+            if (u_ && pl > ukA && pl < ukB) prefetch3d(&tmAuxU, x0 - 2 - G.ub_i0, y0 - 1 - G.ub_j0, pl - G.ub_kl0);
+        }
+    };
+    if (tid == 0)
+        for (int q = 0; q < min(NSTAGE, nload); ++q) issue(q);
+
+    const int sdx = G.sdx, sdz = G.sdz, kdz = G.kdz;
+    const int i0 = x0 + 2 * tx, j = y0 + ty;
+    const bool active = (i0 < sdx) && (j < G.sdy);
+    const bool xlA = (i0 == 0), xhB = (i0 + 2 == sdx), yl = (j == 0), yh = (j == G.sdy - 1);
+    // thread-constant coefficients of non-conductor rows (EC3D.f90:528-654): on a low face the '+'
+    // neighbour carries BND(axis,2)*s, on a high face the '-' neighbour carries BND(axis,1)*s
+    const double cxpA = xlA ? cf.blo[0] : cf.msx;           // cell a's right neighbour (= cell b)
+    const double cxmB = xhB ? cf.bhi[0] : cf.msx;           // cell b's left neighbour (= cell a)
+    const double cym = yh ? cf.bhi[1] : cf.msy, cyp = yl ? cf.blo[1] : cf.msy;
+    const int bxyA = (int)xlA | ((int)(yl | yh) << 1), bxyB = (int)xhB | ((int)(yl | yh) << 1);
+    const double dgA0 = cf.diag_b[bxyA], dgA1 = cf.diag_b[bxyA | 4];   // diag_b[0] == diag_int
+    const double dgB0 = cf.diag_b[bxyB], dgB1 = cf.diag_b[bxyB | 4];
+    const int o_own = (ty + 1) * BW + 2 + 2 * tx;           // own pair inside a halo tile (doubles)
+    const int o_cls = CLS_OFF + ty * TX + 2 * tx;           // own pair's class bytes inside a stage
+    // own pair inside the dense U box footprint?
+    const bool inUxy = tileU && active && i0 >= G.ub_i0 && i0 < G.ub_i0 + G.ub_nx && j >= G.ub_j0 && j < G.ub_j0 + G.ub_ny;
+    const double *__restrict__ auxp = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : nullptr;
+    // running offsets of the pair at the plane computed next (k = kb at q = 2)
+    long long pA = (long long)(kb - G.k0 + 1) * kdz + (long long)j * sdx + i0;                       // A part
+    long long pU = G.offU + (long long)(kb - G.ub_kl0) * G.ub_pl + (long long)(j - G.ub_j0) * G.ub_nx + (i0 - G.ub_i0);
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 m[3] = {zero2, zero2, zero2}, c[3] = {zero2, zero2, zero2};
+    double2 ugm = zero2, ugc = zero2;
+    double a0 = 0.0, a1 = 0.0;
+    int s = 0, sp = 0;                                      // stage of load q, of load q-1
+    uint32_t ph = 0;
+
+    for (int q = 0; q < nload; ++q) {
+        const int k = kb + q - 2;                           // plane computed in this iteration (q >= 2)
+        const bool doit = (q >= 2) && active;
+        // r0 / b of this plane (L2 hits thanks to the prefetch issued with the ring loads)
+        double2 aux[3] = {zero2, zero2, zero2}, auxU = zero2;
+        if (HAS_AUX && doit) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) aux[a] = ld2(auxp + a * G.segA + pA);
+            if (inUxy && k >= G.ub_k0 && k < ukB) auxU = ld2(auxp + pU);
+        }
+        mbar_wait(full + s, ph);
+        const double *xn = reinterpret_cast<const double *>(smem + s * STAGE_BYTES);
+        double2 z1[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) z1[a] = *reinterpret_cast<const double2 *>(xn + a * TILE_D + o_own);
+        double2 ugp = zero2;
+        {
+            const int pl = kb - 1 + q;
+            if (tileU && pl >= ukA && pl <= ukB) ugp = *reinterpret_cast<const double2 *>(xn + US_OFF / 8 + o_own);
+        }
+        if (doit) {
+            const unsigned char *stp = smem + sp * STAGE_BYTES;
+            const double *xs = reinterpret_cast<const double *>(stp);
+            const uchar2 cl = *reinterpret_cast<const uchar2 *>(stp + o_cls);
+            const bool zl = (k == 0), zh = (k == sdz - 1);
+            const double czm = zh ? cf.bhi[2] : cf.msz, czp = zl ? cf.blo[2] : cf.msz;
+            const double dgA = (zl | zh) ? dgA1 : dgA0, dgB = (zl | zh) ? dgB1 : dgB0;
+            const int ca = cl.x, cb = cl.y;
+            if ((ca | cb) == 0) {
+                // ---- both cells are non-conductor ----
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double *t = xs + a * TILE_D + o_own;
+                    const double2 ym = *reinterpret_cast<const double2 *>(t - BW);
+                    const double2 yp = *reinterpret_cast<const double2 *>(t + BW);
+                    const double xm = t[-1], xp = t[2];
+                    const double ya = row7(czm, cym, cf.msx, dgA, cxpA, cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
+                    const double yb = row7(czm, cym, cxmB, dgB, cf.msx, cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
+                    pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
+                }
+            } else {
+                // ---- at least one conductor cell (never on a domain face): generic per-cell rows ----
+                const double *us = xs + US_OFF / 8;
+                const double *Uin = vs.x;                     // dense U box lives in the input vector
+                U5 ua[3], ub[3];                              // U along x / y / z for cell a / b
+                {
+                    const double *t = us + o_own;
+                    ua[0] = U5{t[-2], t[-1], ugc.x, ugc.y, t[2]};
+                    ub[0] = U5{t[-1], ugc.x, ugc.y, t[2], t[3]};
+                    const double2 um = *reinterpret_cast<const double2 *>(t - BW);
+                    const double2 up = *reinterpret_cast<const double2 *>(t + BW);
+                    ua[1] = U5{0.0, um.x, ugc.x, up.x, 0.0};
+                    ub[1] = U5{0.0, um.y, ugc.y, up.y, 0.0};
+                    ua[2] = U5{0.0, ugm.x, ugc.x, ugp.x, 0.0};
+                    ub[2] = U5{0.0, ugm.y, ugc.y, ugp.y, 0.0};
+                    // one-sided gradients along y / z reach two cells: read those from the dense box
+                    const int sya = (ca >> 2) & 3, syb = (cb >> 2) & 3, sza = (ca >> 4) & 3, szb = (cb >> 4) & 3;
+                    if (sya & 2) ua[1].m2 = Uin[pU - 2 * G.ub_nx]; else if (sya & 1) ua[1].p2 = Uin[pU + 2 * G.ub_nx];
+                    if (syb & 2) ub[1].m2 = Uin[pU + 1 - 2 * G.ub_nx]; else if (syb & 1) ub[1].p2 = Uin[pU + 1 + 2 * G.ub_nx];
+                    if (sza & 2) ua[2].m2 = Uin[pU - 2 * G.ub_pl]; else if (sza & 1) ua[2].p2 = Uin[pU + 2 * G.ub_pl];
+                    if (szb & 2) ub[2].m2 = Uin[pU + 1 - 2 * G.ub_pl]; else if (szb & 1) ub[2].p2 = Uin[pU + 1 + 2 * G.ub_pl];
+                }
+                double suA = 0.0, suB = 0.0;                  // running A part of the U rows
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double *t = xs + a * TILE_D + o_own;
+                    const double2 ym = *reinterpret_cast<const double2 *>(t - BW);
+                    const double2 yp = *reinterpret_cast<const double2 *>(t + BW);
+                    const double xm = t[-1], xp = t[2];
+                    double ya, yb;
+                    if (ca) {
+                        const int sa = (ca >> (2 * a)) & 3;
+                        ya = (a == 0) ? cond_a<0>(mc, sa, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x, ua[0])
+                           : (a == 1) ? cond_a<1>(mc, sa, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x, ua[1])
+                                      : cond_a<2>(mc, sa, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x, ua[2]);
+                        const double am = (a == 0) ? xm : (a == 1) ? ym.x : m[a].x;
+                        const double ap = (a == 0) ? c[a].y : (a == 1) ? yp.x : z1[a].x;
+                        suA = (a == 0) ? urow_a<0>(cf, ca, am, c[a].x, ap, suA)
+                            : (a == 1) ? urow_a<1>(cf, ca, am, c[a].x, ap, suA)
+                                       : urow_a<2>(cf, ca, am, c[a].x, ap, suA);
+                    } else {
+                        ya = row7(czm, cym, cf.msx, dgA, cxpA, cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
+                    }
+                    if (cb) {
+                        const int sb = (cb >> (2 * a)) & 3;
+                        yb = (a == 0) ? cond_a<0>(mc, sb, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y, ub[0])
+                           : (a == 1) ? cond_a<1>(mc, sb, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y, ub[1])
+                                      : cond_a<2>(mc, sb, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y, ub[2]);
+                        const double am = (a == 0) ? c[a].x : (a == 1) ? ym.y : m[a].y;
+                        const double ap = (a == 0) ? xp : (a == 1) ? yp.y : z1[a].y;
+                        suB = (a == 0) ? urow_a<0>(cf, cb, am, c[a].y, ap, suB)
+                            : (a == 1) ? urow_a<1>(cf, cb, am, c[a].y, ap, suB)
+                                       : urow_a<2>(cf, cb, am, c[a].y, ap, suB);
+                    } else {
+                        yb = row7(czm, cym, cxmB, dgB, cf.msx, cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
+                    }
+                    pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
+                }
+                // U rows
+                double sa_ = 0.0, sb_ = 0.0;
+                if (ca) sa_ = urow_u(cf, ca, ua[2].m1, ua[1].m1, ua[0].m1, ugc.x, ua[0].p1, ua[1].p1, ua[2].p1, suA);
+                if (cb) sb_ = urow_u(cf, cb, ub[2].m1, ub[1].m1, ub[0].m1, ugc.y, ub[0].p1, ub[1].p1, ub[2].p1, suB);
+                pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { m[a] = c[a]; c[a] = z1[a]; }
+        ugm = ugc; ugc = ugp;
+        if (q >= 2) { pA += kdz; pU += G.ub_pl; }
+        __syncthreads();                                    // every thread is done with stage sp (load q-1)
+        if (tid == 0 && q >= 1 && q - 1 + NSTAGE < nload) issue(q - 1 + NSTAGE);
+        sp = s;
+        if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+    }
+    if (MODE != MODE_PLAIN) {
+        const int pidx = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        const unsigned ex = finalize_here ? expected : 0xffffffffu;
+        if (MODE == MODE_AP)
+            reduce_epilogue<1>(a0, 0.0, partials, pstride, pidx, ex, ctl.sc, RED_APR0, RED_APR0, sh);
+        else if (MODE == MODE_AS)
+            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, ex, ctl.sc, RED_ASS, RED_ASAS, sh);
+        else
+            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, ex, ctl.sc, RED_BB, RED_RR_INIT, sh);
+    }
+}
+
+// reference U numbering (k,j,i order over this rank's conductor cells) <-> dense U box
+__global__ void k_u_unpack(const SlabGeom G, const int *__restrict__ cond_cells, const int ncond,
+                           const double *__restrict__ compact, double *__restrict__ vec)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncond) return;
+    const int cell0 = cond_cells[t];
+    const int k = cell0 / G.kdz, rem = cell0 - k * G.kdz, j = rem / G.sdx, i = rem - j * G.sdx;
+    vec[u_local(G, i, j, k)] = compact[t];
+}
+
+__global__ void k_u_pack(const SlabGeom G, const int *__restrict__ cond_cells, const int ncond,
+                         const double *__restrict__ vec, double *__restrict__ compact)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncond) return;
+    const int cell0 = cond_cells[t];
+    const int k = cell0 / G.kdz, rem = cell0 - k * G.kdz, j = rem / G.sdx, i = rem - j * G.sdx;
+    compact[t] = vec[u_local(G, i, j, k)];
+}

@@ -26,8 +26,8 @@ ITER_TOL = 0.05        # north_star: iteration counts within 5 %
 # distance between the oracle and the SAME oracle with pairwise instead of sequential reductions
 # (oracle.set_dot_mode(1)) -- i.e. it may deviate from the reference no more than the reference
 # deviates from itself under reassociation -- and never by more than REL_L2_DRIFT_CAP.
-DRIFT_FACTOR = 20.0
-REL_L2_DRIFT_CAP = 1e-5
+DRIFT_FACTOR = 10.0
+REL_L2_DRIFT_CAP = 1e-4
 
 
 def rel(a, b):
@@ -221,6 +221,13 @@ def _run_steps(lib, oracle_mod, p, nsteps, golden=None):
 @pytest.mark.parametrize("variant", ["A", "B", "M"])
 def test_timesteps_plate(gpu_lib, oracle_mod, plates, variant):
     _run_steps(gpu_lib, oracle_mod, plates[variant], 5)
+
+
+# A tight-tolerance variant (where both arms would converge to the same solution whatever the
+# summation order) does not exist for this algorithm: the reference's unpreconditioned BiCGSTABwr
+# stagnates on the (gauge-singular) A-U system -- on plate(32) the oracle itself runs into itmax for
+# every tol <= 1e-4 and breaks down to NaN for tol <= 1e-8.  The loose tol = 5e-3 of the shipped decks
+# is the only regime the reference converges in, hence the self-calibrated drift bound above.
 
 
 @pytest.mark.parametrize("deck,nsteps", [("compare_to_Elmer", 3), ("ec_src_move_hole", 3), ("LIM", 6)])
