@@ -415,9 +415,12 @@ struct ec3d_handle {
     MatCoef mc0{};
     bool tma = false;                    // k_spmv_tma usable (even sdx); else k_air_spmv + k_cond_spmv
     int nstage = 4;                      // depth of the TMA ring (EC3D_NSTAGE = 3, 4, 5)
+    int dbg = 0;                         // EC3D_DBG: timing experiments only
     CUtensorMap tmA[EC3D_NVEC], tmU[EC3D_NVEC];   // per local vector: A part (4-D), dense U box (3-D)
+    CUtensorMap tmPA[EC3D_NVEC], tmPU[EC3D_NVEC]; // same tensors with halo-free 64 x 8 boxes (L2 prefetch of r0 / b)
     CUtensorMap tmC;                     // class bytes (3-D, uint8)
     int clsx = 0;                        // row pitch of d_cls (sdx rounded up to 16)
+    WorkItem *d_items = nullptr;         // (tile column, z range) work list of k_spmv_tma
     double *d_ucompact = nullptr;        // staging of the U block in the reference's compact numbering
     long long u_glob0 = 0;               // 0-based global index of this rank's first U unknown
     long long n_unknowns_own = 0;        // owned unknowns (without the padding of the dense U box)
@@ -496,7 +499,7 @@ static void launch_tma(ec3d_handle *h, int v, int vaux, const VecSet &vs, const 
 {
     Solver &s = h->sol;
     k_spmv_tma<MODE, NSTAGE><<<h->airGrid, dim3(32, 8), tma::smem_bytes(NSTAGE), h->st>>>(
-        h->tmA[v], h->tmU[v], h->tmC, h->tmA[vaux], h->tmU[vaux], h->G, h->cf, h->mc0, vs, ctl, h->zc, s.partials,
+        h->tmA[v], h->tmU[v], h->tmC, h->tmPA[vaux], h->tmPU[vaux], h->G, h->cf, h->mc0, h->d_items, vs, ctl, s.partials,
         s.pstride, (unsigned)h->nblkAir, 1);
 }
 
@@ -511,6 +514,14 @@ static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
         const double *auxp = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : vs.x;
         long long va = (auxp - h->vecs) / h->G.ltot;
         if (va < 0 || va >= EC3D_NVEC) va = v;            // (only used for an L2 prefetch)
+        if (h->dbg && MODE == MODE_AS) {               // timing experiments only (EC3D_DBG)
+#define DBGL(D) k_spmv_tma<MODE_AS, 4, D><<<h->airGrid, dim3(32, 8), tma::smem_bytes(4), h->st>>>( \
+            h->tmA[v], h->tmU[v], h->tmC, h->tmPA[va], h->tmPU[va], h->G, h->cf, h->mc0, h->d_items, vs, ctl, s.partials, \
+            s.pstride, (unsigned)h->nblkAir, 1)
+            switch (h->dbg) { case 1: DBGL(1); break; case 7: DBGL(7); break; case 8: DBGL(8); break; case 16: DBGL(16); break;
+                              default: DBGL(32); break; }
+#undef DBGL
+        } else
         switch (h->nstage) {
         case 3: launch_tma<MODE, 3>(h, (int)v, (int)va, vs, ctl); break;
         case 5: launch_tma<MODE, 5>(h, (int)v, (int)va, vs, ctl); break;
@@ -559,7 +570,7 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     if (h->sol.graph) cudaGraphExecDestroy(h->sol.graph);
     if (h->comm) ncclCommDestroy(h->comm);
     cudaFree(h->d_mc); cudaFree(h->d_geo); cudaFree(h->d_mat); cudaFree(h->d_cond_cells); cudaFree(h->d_flags);
-    cudaFree(h->d_cls); cudaFree(h->d_ucompact);
+    cudaFree(h->d_cls); cudaFree(h->d_ucompact); cudaFree(h->d_items);
     cudaFree(h->vecs); cudaFree(h->sol.sc); cudaFree(h->sol.iter_base); cudaFree(h->sol.partials);
     cudaFree(h->d_nod_ptr); cudaFree(h->d_nods); cudaFree(h->d_num_Vmech); cudaFree(h->d_comp);
     cudaFree(h->d_new_nodes); cudaFree(h->d_ms); cudaFree(h->d_fun_vely); cudaFree(h->d_vmech); cudaFree(h->d_oob);
@@ -586,6 +597,8 @@ static int encode_tensor_maps(ec3d_handle *h)
         enc = (PFN_cuTensorMapEncodeTiled_v12000)fn;
     }
     const SlabGeom &G = h->G;
+    const char *el = getenv("EC3D_L2P");
+    const CUtensorMapL2promotion l2p = el ? (CUtensorMapL2promotion)atoi(el) : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     {
         const cuuint64_t gdim[3] = {(cuuint64_t)h->clsx, (cuuint64_t)G.sdy, (cuuint64_t)G.nzl};
         const cuuint64_t gstr[2] = {(cuuint64_t)h->clsx, (cuuint64_t)h->clsx * G.sdy};
@@ -604,9 +617,13 @@ static int encode_tensor_maps(ec3d_handle *h)
             const cuuint32_t box[4] = {tma::BW, tma::BH, 1, 3};
             const cuuint32_t estr[4] = {1, 1, 1, 1};
             const CUresult r = enc(&h->tmA[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, gdim, gstr, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2p,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { ec3d_set_error("cuTensorMapEncodeTiled(A part) failed: %d", (int)r); return EC3D_ERR_CUDA; }
+            const cuuint32_t boxp[4] = {tma::TX, tma::TY, 1, 3};
+            const CUresult r2 = enc(&h->tmPA[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, gdim, gstr, boxp, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r2 != CUDA_SUCCESS) { ec3d_set_error("cuTensorMapEncodeTiled(A part, prefetch box) failed: %d", (int)r2); return EC3D_ERR_CUDA; }
         }
         const int nst = G.ub_kl1 - G.ub_kl0;
         if (nst > 0) {
@@ -618,8 +635,14 @@ static int encode_tensor_maps(ec3d_handle *h)
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { ec3d_set_error("cuTensorMapEncodeTiled(U box) failed: %d", (int)r); return EC3D_ERR_CUDA; }
+            const cuuint32_t boxp[3] = {tma::TX, tma::TY, 1};
+            const CUresult r2 = enc(&h->tmPU[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base + G.offU, gdim, gstr, boxp, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r2 != CUDA_SUCCESS) { ec3d_set_error("cuTensorMapEncodeTiled(U box, prefetch box) failed: %d", (int)r2); return EC3D_ERR_CUDA; }
         } else {
             h->tmU[v] = h->tmA[v];     // never dereferenced: no tile needs U
+            h->tmPU[v] = h->tmA[v];
         }
     }
     return EC3D_OK;
@@ -641,6 +664,9 @@ static cudaError_t set_attr_modes()
 }
 static int set_tma_smem_attr()
 {
+#define DBGA(D) CUDA_TRY(cudaFuncSetAttribute(k_spmv_tma<MODE_AS, 4, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::smem_bytes(4)))
+    DBGA(1); DBGA(7); DBGA(8); DBGA(16); DBGA(32);
+#undef DBGA
     CUDA_TRY(set_attr_modes<3>());
     CUDA_TRY(set_attr_modes<4>());
     CUDA_TRY(set_attr_modes<5>());
@@ -848,6 +874,8 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         h->tma = (sdx % 2 == 0) && !(ef && atoi(ef) == 0);
         const char *en = getenv("EC3D_NSTAGE");
         h->nstage = (en && (atoi(en) == 3 || atoi(en) == 5)) ? atoi(en) : 4;
+        const char *ed = getenv("EC3D_DBG");
+        h->dbg = ed ? atoi(ed) : 0;
     }
     if (h->tma) {
         h->clsx = (sdx + 15) & ~15;
@@ -862,18 +890,74 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         if (rc) return rc;
         rc = set_tma_smem_attr();
         if (rc) return rc;
+        // work list: (tile column, z range) items.  Tile columns that touch the conductor's bounding
+        // box are split at the box's first / last plane so that items are either free of conductor
+        // cells (lean 7-point loop) or carry them (U tiles, class bytes, conductor rows).  Each range is
+        // cut into equal chunks of at most zc planes (zc/2 for ranges with conductor cells, which cost
+        // about twice as much per plane).  An item loads 2 planes more than it computes and pays one
+        // pipeline fill, so long chunks are cheaper -- but CTAs are latency bound, the hardware hands
+        // items out in blockIdx order to 2 x 148 CTA slots, and the last round must not be half empty.
+        // zc is therefore chosen by simulating that list schedule with a simple cost model.
         const int tx = (sdx + tma::TX - 1) / tma::TX, ty = (sdy + tma::TY - 1) / tma::TY;
-        const int tiles = tx * ty;
-        // z chunks: about two rounds of 2 CTAs/SM keep the z-halo re-reads (2 planes per chunk) small
-        // while leaving enough CTAs in the last round to keep HBM busy
-        const int nzch_want = std::max(1, (2 * 2 * 148 + tiles / 2) / tiles);
-        int zc = std::max(std::min(G.nzl, 4), (G.nzl + nzch_want - 1) / nzch_want);
-        const char *ez = getenv("EC3D_ZC");
-        if (ez && atoi(ez) > 0) zc = atoi(ez);
+        const int ck0 = std::max(G.k0, G.ub_k0), ck1 = std::min(G.k1, G.ub_k0 + G.ub_nz);   // conductor planes of this slab
+        auto build_items = [&](int zc, std::vector<WorkItem> &items) {
+            std::vector<WorkItem> light;
+            items.clear();
+            for (int by = 0; by < ty; ++by)
+                for (int bx = 0; bx < tx; ++bx) {
+                    const int x0 = bx * tma::TX, y0 = by * tma::TY;
+                    const bool touch = G.ub_nz > 0 && ck1 > ck0 && x0 < G.ub_i0 + G.ub_nx && x0 + tma::TX > G.ub_i0 &&
+                                       y0 < G.ub_j0 + G.ub_ny && y0 + tma::TY > G.ub_j0;
+                    const int cuts[4] = {G.k0, touch ? ck0 : G.k1, touch ? ck1 : G.k1, G.k1};
+                    for (int r = 0; r < 3; ++r) {
+                        const int ra = cuts[r], rb = cuts[r + 1];
+                        if (rb <= ra) continue;
+                        const int has_u = (touch && r == 1) ? 1 : 0;
+                        const int zmax = has_u ? std::max(4, zc / 2) : zc;
+                        const int nch = (rb - ra + zmax - 1) / zmax, len = (rb - ra + nch - 1) / nch;
+                        for (int ka = ra; ka < rb; ka += len)
+                            (has_u ? items : light).push_back(WorkItem{x0, y0, ka, std::min(ka + len, rb), has_u, 0, 0, 0});
+                    }
+                }
+            items.insert(items.end(), light.begin(), light.end());   // items with conductor cells are scheduled first
+        };
+        auto makespan = [&](const std::vector<WorkItem> &items) {
+            const int slots = 2 * 148;
+            std::vector<double> freeat(slots, 0.0);        // min-heap by hand: slots is small
+            std::make_heap(freeat.begin(), freeat.end(), std::greater<double>());
+            double end = 0.0;
+            for (const WorkItem &w : items) {
+                std::pop_heap(freeat.begin(), freeat.end(), std::greater<double>());
+                const double cost = 2.5 + (w.ke - w.kb) * (w.has_u ? 2.5 : 1.0) + 2.0 * 0.35;   // fill + planes + 2 halo loads
+                freeat.back() += cost;
+                end = std::max(end, freeat.back());
+                std::push_heap(freeat.begin(), freeat.end(), std::greater<double>());
+            }
+            return end;
+        };
+        std::vector<WorkItem> items, cand;
+        int zc = 0;
+        {
+            const char *ez = getenv("EC3D_ZC");
+            if (ez && atoi(ez) > 0) {
+                zc = atoi(ez);
+                build_items(zc, items);
+            } else {
+                double best = 0.0;
+                for (int z = std::min(8, G.nzl); z <= std::min(96, G.nzl); ++z) {
+                    build_items(z, cand);
+                    const double t = makespan(cand);
+                    if (zc == 0 || t < best * 0.995) { best = t; zc = z; items.swap(cand); }
+                }
+            }
+        }
         h->zc = zc;
-        const int nzch = (G.nzl + zc - 1) / zc;
-        h->airGrid = dim3(tx, ty, nzch);
-        h->nblkAir = tiles * nzch;
+        if (getenv("EC3D_VERBOSE")) fprintf(stderr, "ec3d: TMA SpMV work list: zc = %d, %zu items\n", zc, items.size());
+        std::vector<WorkItem> &heavy = items;
+        CUDA_TRY(cudaMalloc(&h->d_items, heavy.size() * sizeof(WorkItem)));
+        CUDA_TRY(cudaMemcpy(h->d_items, heavy.data(), heavy.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+        h->airGrid = dim3((unsigned)heavy.size());
+        h->nblkAir = (int)heavy.size();
         h->nblkCond = 0;
         if (h->nblkAir + 8 > s.pstride) {
             cudaFree(s.partials);

@@ -253,198 +253,308 @@ __device__ __forceinline__ double row7(const double czm, const double cym, const
     return y;
 }
 
-template <int MODE, int NSTAGE>
+// One work item of the TMA SpMV: a 64 x 8 tile column and a z range.  has_u != 0 when the item
+// contains conductor cells (then U tiles and class bytes are staged and the generic row code runs);
+// items without conductor cells run a lean 7-point loop.  Built on the host (build_work_items).
+struct WorkItem {
+    int x0, y0, kb, ke;     // tile origin, owned planes [kb, ke)
+    int has_u, pad0, pad1, pad2;
+};
+
+struct TmaCtx {             // per-thread constants of k_spmv_tma
+    int tx, ty, lane, warp;
+    int x0, y0, kb, ke, nload;
+    int o_own, o_cls;
+    bool active, inUxy;
+    double cxpA, cxmB, cym, cyp, dgA0, dgA1, dgB0, dgB1;
+};
+
+// Plane loop of one work item.  HAS_U = item contains conductor cells.
+template <int MODE, int NSTAGE, bool HAS_U, int DBG>
+__device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUtensorMap &tmU, const CUtensorMap &tmC,
+                                               const CUtensorMap &tmAuxA, const CUtensorMap &tmAuxU, const SlabGeom &G,
+                                               const Coef &cf, const MatCoef &mc, const VecSet &vs, const TmaCtx &t,
+                                               unsigned char *smem, unsigned long long *full, unsigned *cnt,
+                                               double &a0, double &a1)
+{
+    using namespace tma;
+    constexpr bool HAS_AUX = (MODE == MODE_AP || MODE == MODE_INIT);
+    const int ukA = G.ub_k0 - 1, ukB = G.ub_k0 + G.ub_nz;   // U tiles are needed for planes [ukA, ukB]
+    const int kb = t.kb, ke = t.ke, nload = t.nload, x0 = t.x0, y0 = t.y0;
+    const int sdx = G.sdx, sdz = G.sdz, kdz = G.kdz;
+    const int i0 = x0 + 2 * t.tx, j = y0 + t.ty;
+    const int o_own = t.o_own;
+
+    auto issue = [&](int q) {                               // q-th plane of this item: pl = kb-1+q
+        const int pl = kb - 1 + q, s = q % NSTAGE;
+        unsigned char *st = smem + s * STAGE_BYTES;
+        const bool u_ = HAS_U && pl >= ukA && pl <= ukB;
+        const bool c_ = pl >= kb && pl < ke;                // planes that are computed
+        mbar_expect_tx(full + s, XS_BYTES + (u_ ? TILE_BYTES : 0) + ((HAS_U && c_) ? CLS_BYTES : 0));
+        load4d(st, &tmX, full + s, x0 - 2, y0 - 1, pl - G.k0 + 1, 0);
+        if (u_) load3d(st + US_OFF, &tmU, full + s, x0 - 2 - G.ub_i0, y0 - 1 - G.ub_j0, pl - G.ub_kl0);
+        if (HAS_U && c_) load3d(st + CLS_OFF, &tmC, full + s, x0, y0, pl - G.k0);
+        if (HAS_AUX && c_) {                                // r0 / b of that plane: pull into L2 ahead of the LDGs
+            prefetch4d(&tmAuxA, x0, y0, pl - G.k0 + 1, 0);      // 64 x 8 x 1 x 3 box, no halo
+            if (u_ && pl > ukA && pl < ukB) prefetch3d(&tmAuxU, x0 - G.ub_i0, y0 - G.ub_j0, pl - G.ub_kl0);
+        }
+    };
+    if (t.warp == 0 && t.lane == 0)
+        for (int q = 0; q < min(NSTAGE, nload); ++q) issue(q);
+
+    // A warp is done with the tiles of load ql: the last of the 8 warps to say so re-arms that stage
+    // with load ql + NSTAGE.  No CTA-wide barrier: warps drift apart by up to the ring depth.
+    auto release = [&](int ql) {
+        __syncwarp();
+        if (t.lane == 0) {
+            const int s = ql % NSTAGE;
+            unsigned old;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt + s)) : "memory");
+            if (old == 7u) {
+                cnt[s] = 0u;
+                if (ql + NSTAGE < nload) issue(ql + NSTAGE);
+            }
+        }
+    };
+
+    const double *__restrict__ auxp = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : nullptr;
+    // offsets of the pair at the plane computed next (k = kb first)
+    long long pA = (long long)(kb - G.k0 + 1) * kdz + (long long)j * sdx + i0;
+    long long pU = G.offU + (long long)(kb - G.ub_kl0) * G.ub_pl + (long long)(j - G.ub_j0) * G.ub_nx + (i0 - G.ub_i0);
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 pl3[3][3];                                      // [slot][component]: planes k-1, k, k+1 rotate through the slots
+    double2 ug3[3] = {zero2, zero2, zero2};                 // same for U
+    int s = 0;                                              // stage of load q
+    uint32_t ph = 0;
+
+    auto own_pair = [&](int slot, int q) {                  // wait for load q, read the own pair into `slot`
+        mbar_wait(full + s, ph);
+        const double *xn = reinterpret_cast<const double *>(smem + s * STAGE_BYTES);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pl3[slot][a] = *reinterpret_cast<const double2 *>(xn + a * TILE_D + o_own);
+        if (HAS_U) {
+            const int pl = kb - 1 + q;
+            ug3[slot] = (pl >= ukA && pl <= ukB) ? *reinterpret_cast<const double2 *>(xn + US_OFF / 8 + o_own) : zero2;
+        }
+    };
+    auto advance = [&]() { if (++s == NSTAGE) { s = 0; ph ^= 1u; } };
+
+    // loads 0 and 1: planes kb-1, kb
+    own_pair(0, 0); advance();
+    own_pair(1, 1); release(0); advance();
+
+    const int nz = ke - kb;
+    for (int it = 0; it < nz; it += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            if (it + u < nz) {
+                const int q = it + u + 2;
+                const int k = kb + it + u;                   // plane computed now
+                const int sm_ = u % 3, sc_ = (u + 1) % 3, sz_ = (u + 2) % 3;   // slots of planes k-1, k, k+1
+                double2 aux[3] = {zero2, zero2, zero2}, auxU = zero2;
+                if (HAS_AUX && t.active) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) aux[a] = ld2(auxp + a * G.segA + pA);
+                    if (HAS_U && t.inUxy && k >= G.ub_k0 && k < ukB) auxU = ld2(auxp + pU);
+                }
+                const int sprev = (s == 0) ? NSTAGE - 1 : s - 1;
+                own_pair(sz_, q);
+                if (t.active) {
+                    const unsigned char *stp = smem + sprev * STAGE_BYTES;
+                    const double *xs = reinterpret_cast<const double *>(stp);
+                    const bool zl = (k == 0), zh = (k == sdz - 1);
+                    const double czm = zh ? cf.bhi[2] : cf.msz, czp = zl ? cf.blo[2] : cf.msz;
+                    const double dgA = (zl | zh) ? t.dgA1 : t.dgA0, dgB = (zl | zh) ? t.dgB1 : t.dgB0;
+                    const double2 *m = pl3[sm_], *c = pl3[sc_], *z1 = pl3[sz_];
+                    int ca = 0, cb = 0;
+                    if (HAS_U) {
+                        const uchar2 cl = *reinterpret_cast<const uchar2 *>(stp + t.o_cls);
+                        ca = cl.x; cb = cl.y;
+                    }
+                    if (!HAS_U || (ca | cb) == 0) {
+                        // ---- both cells are non-conductor ----
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            const double *tt = xs + a * TILE_D + o_own;
+                            const double2 ym = (DBG & 4) ? m[a] : *reinterpret_cast<const double2 *>(tt - BW);
+                            const double2 yp = (DBG & 4) ? z1[a] : *reinterpret_cast<const double2 *>(tt + BW);
+                            const double xm = (DBG & 4) ? c[a].y : tt[-1], xp = (DBG & 4) ? c[a].x : tt[2];
+                            double ya, yb;
+                            if (DBG & 2) {
+                                ya = DADD(DADD(DADD(m[a].x, ym.x), DADD(xm, c[a].x)), DADD(yp.x, z1[a].x));
+                                yb = DADD(DADD(DADD(m[a].y, ym.y), DADD(xp, c[a].y)), DADD(yp.y, z1[a].y));
+                            } else {
+                                ya = row7(czm, t.cym, cf.msx, dgA, t.cxpA, t.cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
+                                yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
+                            }
+                            if (DBG & 1) { a0 = DADD(a0, ya); a1 = DADD(a1, yb); }
+                            else pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
+                        }
+                    } else if (ca == 0x40 && cb == 0x40) {
+                        // ---- both cells are interior conductor cells (all six neighbours conductor):
+                        //      central grad U in the A rows (EC3D.f90:677-679), 13-entry U rows (:917-922) ----
+                        const double2 ugm = ug3[sm_], ugc = ug3[sc_], ugp = ug3[sz_];
+                        const double *tu = xs + US_OFF / 8 + o_own;
+                        const double uxm = tu[-1], uxp = tu[2];
+                        const double2 uym = *reinterpret_cast<const double2 *>(tu - BW);
+                        const double2 uyp = *reinterpret_cast<const double2 *>(tu + BW);
+                        double suA = 0.0, suB = 0.0;              // running A part of the U rows
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            const double *tt = xs + a * TILE_D + o_own;
+                            const double2 ym = *reinterpret_cast<const double2 *>(tt - BW);
+                            const double2 yp = *reinterpret_cast<const double2 *>(tt + BW);
+                            const double xm = tt[-1], xp = tt[2];
+                            double ya = row7(mc.cm[2], mc.cm[1], mc.cm[0], mc.diag, mc.cp[0], mc.cp[1], mc.cp[2], m[a].x, ym.x, xm,
+                                             c[a].x, c[a].y, yp.x, z1[a].x);
+                            double yb = row7(mc.cm[2], mc.cm[1], mc.cm[0], mc.diag, mc.cp[0], mc.cp[1], mc.cp[2], m[a].y, ym.y, c[a].x,
+                                             c[a].y, xp, yp.y, z1[a].y);
+                            // U(-1), U(+1) and A(-1), A(+1) along this component's axis
+                            const double umA = (a == 0) ? uxm : (a == 1) ? uym.x : ugm.x;
+                            const double upA = (a == 0) ? ugc.y : (a == 1) ? uyp.x : ugp.x;
+                            const double umB = (a == 0) ? ugc.x : (a == 1) ? uym.y : ugm.y;
+                            const double upB = (a == 0) ? uxp : (a == 1) ? uyp.y : ugp.y;
+                            ya = DADD(ya, DMUL(mc.g1[a], umA)); ya = DADD(ya, DMUL(-mc.g1[a], upA));
+                            yb = DADD(yb, DMUL(mc.g1[a], umB)); yb = DADD(yb, DMUL(-mc.g1[a], upB));
+                            const double amA = (a == 0) ? xm : (a == 1) ? ym.x : m[a].x;
+                            const double apA = (a == 0) ? c[a].y : (a == 1) ? yp.x : z1[a].x;
+                            const double amB = (a == 0) ? c[a].x : (a == 1) ? ym.y : m[a].y;
+                            const double apB = (a == 0) ? xp : (a == 1) ? yp.y : z1[a].y;
+                            suA = DADD(suA, DMUL(cf.ua_p[a], amA)); suA = DADD(suA, DMUL(cf.ua_m[a], apA));
+                            suB = DADD(suB, DMUL(cf.ua_p[a], amB)); suB = DADD(suB, DMUL(cf.ua_m[a], apB));
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
+                        }
+                        // U columns k-1, j-1, i-1, centre, i+1, j+1, k+1
+                        suA = DADD(suA, DMUL(cf.msz, ugm.x)); suB = DADD(suB, DMUL(cf.msz, ugm.y));
+                        suA = DADD(suA, DMUL(cf.msy, uym.x)); suB = DADD(suB, DMUL(cf.msy, uym.y));
+                        suA = DADD(suA, DMUL(cf.msx, uxm));   suB = DADD(suB, DMUL(cf.msx, ugc.x));
+                        suA = DADD(suA, DMUL(cf.diag_int, ugc.x)); suB = DADD(suB, DMUL(cf.diag_int, ugc.y));
+                        suA = DADD(suA, DMUL(cf.msx, ugc.y)); suB = DADD(suB, DMUL(cf.msx, uxp));
+                        suA = DADD(suA, DMUL(cf.msy, uyp.x)); suB = DADD(suB, DMUL(cf.msy, uyp.y));
+                        suA = DADD(suA, DMUL(cf.msz, ugp.x)); suB = DADD(suB, DMUL(cf.msz, ugp.y));
+                        pair_out<MODE>(suA, suB, true, true, pU, ugc.x, ugc.y, auxU, vs, a0, a1);
+                    } else {
+                        // ---- conductor-surface cells / mixed pairs (never on a domain face): generic per-cell rows ----
+                        const double2 ugm = ug3[sm_], ugc = ug3[sc_], ugp = ug3[sz_];
+                        const double *us = xs + US_OFF / 8;
+                        const double *Uin = vs.x;                 // dense U box lives in the input vector
+                        U5 ua[3], ub[3];                          // U along x / y / z for cell a / b
+                        {
+                            const double *tt = us + o_own;
+                            ua[0] = U5{tt[-2], tt[-1], ugc.x, ugc.y, tt[2]};
+                            ub[0] = U5{tt[-1], ugc.x, ugc.y, tt[2], tt[3]};
+                            const double2 um = *reinterpret_cast<const double2 *>(tt - BW);
+                            const double2 up = *reinterpret_cast<const double2 *>(tt + BW);
+                            ua[1] = U5{0.0, um.x, ugc.x, up.x, 0.0};
+                            ub[1] = U5{0.0, um.y, ugc.y, up.y, 0.0};
+                            ua[2] = U5{0.0, ugm.x, ugc.x, ugp.x, 0.0};
+                            ub[2] = U5{0.0, ugm.y, ugc.y, ugp.y, 0.0};
+                            // one-sided gradients along y / z reach two cells: read those from the dense box
+                            const int sya = (ca >> 2) & 3, syb = (cb >> 2) & 3, sza = (ca >> 4) & 3, szb = (cb >> 4) & 3;
+                            if (sya & 2) ua[1].m2 = Uin[pU - 2 * G.ub_nx]; else if (sya & 1) ua[1].p2 = Uin[pU + 2 * G.ub_nx];
+                            if (syb & 2) ub[1].m2 = Uin[pU + 1 - 2 * G.ub_nx]; else if (syb & 1) ub[1].p2 = Uin[pU + 1 + 2 * G.ub_nx];
+                            if (sza & 2) ua[2].m2 = Uin[pU - 2 * G.ub_pl]; else if (sza & 1) ua[2].p2 = Uin[pU + 2 * G.ub_pl];
+                            if (szb & 2) ub[2].m2 = Uin[pU + 1 - 2 * G.ub_pl]; else if (szb & 1) ub[2].p2 = Uin[pU + 1 + 2 * G.ub_pl];
+                        }
+                        double suA = 0.0, suB = 0.0;              // running A part of the U rows
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            const double *tt = xs + a * TILE_D + o_own;
+                            const double2 ym = *reinterpret_cast<const double2 *>(tt - BW);
+                            const double2 yp = *reinterpret_cast<const double2 *>(tt + BW);
+                            const double xm = tt[-1], xp = tt[2];
+                            double ya, yb;
+                            if (ca) {
+                                const int sa = (ca >> (2 * a)) & 3;
+                                ya = (a == 0) ? cond_a<0>(mc, sa, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x, ua[0])
+                                   : (a == 1) ? cond_a<1>(mc, sa, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x, ua[1])
+                                              : cond_a<2>(mc, sa, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x, ua[2]);
+                                const double am = (a == 0) ? xm : (a == 1) ? ym.x : m[a].x;
+                                const double ap = (a == 0) ? c[a].y : (a == 1) ? yp.x : z1[a].x;
+                                suA = (a == 0) ? urow_a<0>(cf, ca, am, c[a].x, ap, suA)
+                                    : (a == 1) ? urow_a<1>(cf, ca, am, c[a].x, ap, suA)
+                                               : urow_a<2>(cf, ca, am, c[a].x, ap, suA);
+                            } else {
+                                ya = row7(czm, t.cym, cf.msx, dgA, t.cxpA, t.cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
+                            }
+                            if (cb) {
+                                const int sb = (cb >> (2 * a)) & 3;
+                                yb = (a == 0) ? cond_a<0>(mc, sb, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y, ub[0])
+                                   : (a == 1) ? cond_a<1>(mc, sb, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y, ub[1])
+                                              : cond_a<2>(mc, sb, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y, ub[2]);
+                                const double am = (a == 0) ? c[a].x : (a == 1) ? ym.y : m[a].y;
+                                const double ap = (a == 0) ? xp : (a == 1) ? yp.y : z1[a].y;
+                                suB = (a == 0) ? urow_a<0>(cf, cb, am, c[a].y, ap, suB)
+                                    : (a == 1) ? urow_a<1>(cf, cb, am, c[a].y, ap, suB)
+                                               : urow_a<2>(cf, cb, am, c[a].y, ap, suB);
+                            } else {
+                                yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
+                            }
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
+                        }
+                        // U rows
+                        double sa_ = 0.0, sb_ = 0.0;
+                        if (ca) sa_ = urow_u(cf, ca, ua[2].m1, ua[1].m1, ua[0].m1, ugc.x, ua[0].p1, ua[1].p1, ua[2].p1, suA);
+                        if (cb) sb_ = urow_u(cf, cb, ub[2].m1, ub[1].m1, ub[0].m1, ugc.y, ub[0].p1, ub[1].p1, ub[2].p1, suB);
+                        pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1);
+                    }
+                }
+                pA += kdz; pU += G.ub_pl;
+                release(q - 1);
+                advance();
+            }
+        }
+    }
+}
+
+template <int MODE, int NSTAGE, int DBG = 0>
 __global__ void __launch_bounds__(256, 2)
 k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmU,
            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAuxA,
            const __grid_constant__ CUtensorMap tmAuxU, const SlabGeom G, const Coef cf, const MatCoef mc,
-           const VecSet vs, const IterCtl ctl, const int zc, double *partials, const int pstride,
+           const WorkItem *__restrict__ items, const VecSet vs, const IterCtl ctl, double *partials, const int pstride,
            const unsigned expected, const int finalize_here)
 {
     using namespace tma;
     extern __shared__ unsigned char smem_raw[];
     __shared__ double sh[32];
     __shared__ __align__(8) unsigned long long full[NSTAGE];
+    __shared__ unsigned cnt[NSTAGE];
     if (!spmv_guard<MODE>(ctl)) return;
     unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = tx + 32 * ty;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int kb = G.k0 + blockIdx.z * zc;
-    const int ke = min(kb + zc, G.k1);
-    const int nload = (ke - kb) + 2;                        // planes kb-1 .. ke
-    constexpr bool HAS_AUX = (MODE == MODE_AP || MODE == MODE_INIT);
-    // does this tile column touch the conductor's bounding box?
-    const bool tileU = (G.ub_nz > 0) && (x0 < G.ub_i0 + G.ub_nx) && (x0 + TX > G.ub_i0) && (y0 < G.ub_j0 + G.ub_ny) &&
-                       (y0 + TY > G.ub_j0);
-    const int ukA = G.ub_k0 - 1, ukB = G.ub_k0 + G.ub_nz;  // U tiles are needed for planes [ukA, ukB]
+    const WorkItem w = items[blockIdx.x];
+    TmaCtx t;
+    t.tx = threadIdx.x; t.ty = threadIdx.y; t.lane = threadIdx.x; t.warp = threadIdx.y;
+    t.x0 = w.x0; t.y0 = w.y0; t.kb = w.kb; t.ke = w.ke; t.nload = (w.ke - w.kb) + 2;
+    const int i0 = t.x0 + 2 * t.tx, j = t.y0 + t.ty;
+    t.active = (i0 < G.sdx) && (j < G.sdy);
+    const bool xlA = (i0 == 0), xhB = (i0 + 2 == G.sdx), yl = (j == 0), yh = (j == G.sdy - 1);
+    // thread-constant coefficients of non-conductor rows (EC3D.f90:528-654): on a low face the '+'
+    // neighbour carries BND(axis,2)*s, on a high face the '-' neighbour carries BND(axis,1)*s
+    t.cxpA = xlA ? cf.blo[0] : cf.msx;                      // cell a's right neighbour (= cell b)
+    t.cxmB = xhB ? cf.bhi[0] : cf.msx;                      // cell b's left neighbour (= cell a)
+    t.cym = yh ? cf.bhi[1] : cf.msy; t.cyp = yl ? cf.blo[1] : cf.msy;
+    const int bxyA = (int)xlA | ((int)(yl | yh) << 1), bxyB = (int)xhB | ((int)(yl | yh) << 1);
+    t.dgA0 = cf.diag_b[bxyA]; t.dgA1 = cf.diag_b[bxyA | 4];   // diag_b[0] == diag_int
+    t.dgB0 = cf.diag_b[bxyB]; t.dgB1 = cf.diag_b[bxyB | 4];
+    t.o_own = (t.ty + 1) * BW + 2 + 2 * t.tx;               // own pair inside a halo tile (doubles)
+    t.o_cls = CLS_OFF + t.ty * TX + 2 * t.tx;               // own pair's class bytes inside a stage
+    t.inUxy = t.active && i0 >= G.ub_i0 && i0 < G.ub_i0 + G.ub_nx && j >= G.ub_j0 && j < G.ub_j0 + G.ub_ny;
 
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(full + s, 1);
+    if (t.warp == 0 && t.lane == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); cnt[s] = 0u; }
         fence_barrier_init();
         fence_proxy_async();
     }
     __syncthreads();
 
-    auto issue = [&](int q) {                               // q-th plane of this chunk: pl = kb-1+q
-        const int pl = kb - 1 + q, s = q % NSTAGE;
-        unsigned char *st = smem + s * STAGE_BYTES;
-        const bool u_ = tileU && pl >= ukA && pl <= ukB;
-        const bool c_ = pl >= kb && pl < ke;                // class bytes only for planes that are computed
-        mbar_expect_tx(full + s, XS_BYTES + (u_ ? TILE_BYTES : 0) + (c_ ? CLS_BYTES : 0));
-        load4d(st, &tmX, full + s, x0 - 2, y0 - 1, pl - G.k0 + 1, 0);
-        if (u_) load3d(st + US_OFF, &tmU, full + s, x0 - 2 - G.ub_i0, y0 - 1 - G.ub_j0, pl - G.ub_kl0);
-        if (c_) load3d(st + CLS_OFF, &tmC, full + s, x0, y0, pl - G.k0);
-        if (HAS_AUX && c_) {                                // r0 / b of that plane: pull into L2 ahead of the LDGs
-            prefetch4d(&tmAuxA, x0 - 2, y0 - 1, pl - G.k0 + 1, 0);
-            if (u_ && pl > ukA && pl < ukB) prefetch3d(&tmAuxU, x0 - 2 - G.ub_i0, y0 - 1 - G.ub_j0, pl - G.ub_kl0);
-        }
-    };
-    if (tid == 0)
-        for (int q = 0; q < min(NSTAGE, nload); ++q) issue(q);
-
-    const int sdx = G.sdx, sdz = G.sdz, kdz = G.kdz;
-    const int i0 = x0 + 2 * tx, j = y0 + ty;
-    const bool active = (i0 < sdx) && (j < G.sdy);
-    const bool xlA = (i0 == 0), xhB = (i0 + 2 == sdx), yl = (j == 0), yh = (j == G.sdy - 1);
-    // thread-constant coefficients of non-conductor rows (EC3D.f90:528-654): on a low face the '+'
-    // neighbour carries BND(axis,2)*s, on a high face the '-' neighbour carries BND(axis,1)*s
-    const double cxpA = xlA ? cf.blo[0] : cf.msx;           // cell a's right neighbour (= cell b)
-    const double cxmB = xhB ? cf.bhi[0] : cf.msx;           // cell b's left neighbour (= cell a)
-    const double cym = yh ? cf.bhi[1] : cf.msy, cyp = yl ? cf.blo[1] : cf.msy;
-    const int bxyA = (int)xlA | ((int)(yl | yh) << 1), bxyB = (int)xhB | ((int)(yl | yh) << 1);
-    const double dgA0 = cf.diag_b[bxyA], dgA1 = cf.diag_b[bxyA | 4];   // diag_b[0] == diag_int
-    const double dgB0 = cf.diag_b[bxyB], dgB1 = cf.diag_b[bxyB | 4];
-    const int o_own = (ty + 1) * BW + 2 + 2 * tx;           // own pair inside a halo tile (doubles)
-    const int o_cls = CLS_OFF + ty * TX + 2 * tx;           // own pair's class bytes inside a stage
-    // own pair inside the dense U box footprint?
-    const bool inUxy = tileU && active && i0 >= G.ub_i0 && i0 < G.ub_i0 + G.ub_nx && j >= G.ub_j0 && j < G.ub_j0 + G.ub_ny;
-    const double *__restrict__ auxp = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : nullptr;
-    // running offsets of the pair at the plane computed next (k = kb at q = 2)
-    long long pA = (long long)(kb - G.k0 + 1) * kdz + (long long)j * sdx + i0;                       // A part
-    long long pU = G.offU + (long long)(kb - G.ub_kl0) * G.ub_pl + (long long)(j - G.ub_j0) * G.ub_nx + (i0 - G.ub_i0);
-    const double2 zero2 = make_double2(0.0, 0.0);
-    double2 m[3] = {zero2, zero2, zero2}, c[3] = {zero2, zero2, zero2};
-    double2 ugm = zero2, ugc = zero2;
     double a0 = 0.0, a1 = 0.0;
-    int s = 0, sp = 0;                                      // stage of load q, of load q-1
-    uint32_t ph = 0;
+    if ((DBG & 16) && !w.has_u) return;                  // timing experiment: heavy items only
+    if (w.has_u && !(DBG & 8)) tma_plane_loop<MODE, NSTAGE, true, DBG>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
+    else if (!((DBG & 32) && w.has_u)) tma_plane_loop<MODE, NSTAGE, false, DBG>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
 
-    for (int q = 0; q < nload; ++q) {
-        const int k = kb + q - 2;                           // plane computed in this iteration (q >= 2)
-        const bool doit = (q >= 2) && active;
-        // r0 / b of this plane (L2 hits thanks to the prefetch issued with the ring loads)
-        double2 aux[3] = {zero2, zero2, zero2}, auxU = zero2;
-        if (HAS_AUX && doit) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) aux[a] = ld2(auxp + a * G.segA + pA);
-            if (inUxy && k >= G.ub_k0 && k < ukB) auxU = ld2(auxp + pU);
-        }
-        mbar_wait(full + s, ph);
-        const double *xn = reinterpret_cast<const double *>(smem + s * STAGE_BYTES);
-        double2 z1[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) z1[a] = *reinterpret_cast<const double2 *>(xn + a * TILE_D + o_own);
-        double2 ugp = zero2;
-        {
-            const int pl = kb - 1 + q;
-            if (tileU && pl >= ukA && pl <= ukB) ugp = *reinterpret_cast<const double2 *>(xn + US_OFF / 8 + o_own);
-        }
-        if (doit) {
-            const unsigned char *stp = smem + sp * STAGE_BYTES;
-            const double *xs = reinterpret_cast<const double *>(stp);
-            const uchar2 cl = *reinterpret_cast<const uchar2 *>(stp + o_cls);
-            const bool zl = (k == 0), zh = (k == sdz - 1);
-            const double czm = zh ? cf.bhi[2] : cf.msz, czp = zl ? cf.blo[2] : cf.msz;
-            const double dgA = (zl | zh) ? dgA1 : dgA0, dgB = (zl | zh) ? dgB1 : dgB0;
-            const int ca = cl.x, cb = cl.y;
-            if ((ca | cb) == 0) {
-                // ---- both cells are non-conductor ----
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const double *t = xs + a * TILE_D + o_own;
-                    const double2 ym = *reinterpret_cast<const double2 *>(t - BW);
-                    const double2 yp = *reinterpret_cast<const double2 *>(t + BW);
-                    const double xm = t[-1], xp = t[2];
-                    const double ya = row7(czm, cym, cf.msx, dgA, cxpA, cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
-                    const double yb = row7(czm, cym, cxmB, dgB, cf.msx, cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
-                    pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
-                }
-            } else {
-                // ---- at least one conductor cell (never on a domain face): generic per-cell rows ----
-                const double *us = xs + US_OFF / 8;
-                const double *Uin = vs.x;                     // dense U box lives in the input vector
-                U5 ua[3], ub[3];                              // U along x / y / z for cell a / b
-                {
-                    const double *t = us + o_own;
-                    ua[0] = U5{t[-2], t[-1], ugc.x, ugc.y, t[2]};
-                    ub[0] = U5{t[-1], ugc.x, ugc.y, t[2], t[3]};
-                    const double2 um = *reinterpret_cast<const double2 *>(t - BW);
-                    const double2 up = *reinterpret_cast<const double2 *>(t + BW);
-                    ua[1] = U5{0.0, um.x, ugc.x, up.x, 0.0};
-                    ub[1] = U5{0.0, um.y, ugc.y, up.y, 0.0};
-                    ua[2] = U5{0.0, ugm.x, ugc.x, ugp.x, 0.0};
-                    ub[2] = U5{0.0, ugm.y, ugc.y, ugp.y, 0.0};
-                    // one-sided gradients along y / z reach two cells: read those from the dense box
-                    const int sya = (ca >> 2) & 3, syb = (cb >> 2) & 3, sza = (ca >> 4) & 3, szb = (cb >> 4) & 3;
-                    if (sya & 2) ua[1].m2 = Uin[pU - 2 * G.ub_nx]; else if (sya & 1) ua[1].p2 = Uin[pU + 2 * G.ub_nx];
-                    if (syb & 2) ub[1].m2 = Uin[pU + 1 - 2 * G.ub_nx]; else if (syb & 1) ub[1].p2 = Uin[pU + 1 + 2 * G.ub_nx];
-                    if (sza & 2) ua[2].m2 = Uin[pU - 2 * G.ub_pl]; else if (sza & 1) ua[2].p2 = Uin[pU + 2 * G.ub_pl];
-                    if (szb & 2) ub[2].m2 = Uin[pU + 1 - 2 * G.ub_pl]; else if (szb & 1) ub[2].p2 = Uin[pU + 1 + 2 * G.ub_pl];
-                }
-                double suA = 0.0, suB = 0.0;                  // running A part of the U rows
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const double *t = xs + a * TILE_D + o_own;
-                    const double2 ym = *reinterpret_cast<const double2 *>(t - BW);
-                    const double2 yp = *reinterpret_cast<const double2 *>(t + BW);
-                    const double xm = t[-1], xp = t[2];
-                    double ya, yb;
-                    if (ca) {
-                        const int sa = (ca >> (2 * a)) & 3;
-                        ya = (a == 0) ? cond_a<0>(mc, sa, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x, ua[0])
-                           : (a == 1) ? cond_a<1>(mc, sa, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x, ua[1])
-                                      : cond_a<2>(mc, sa, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x, ua[2]);
-                        const double am = (a == 0) ? xm : (a == 1) ? ym.x : m[a].x;
-                        const double ap = (a == 0) ? c[a].y : (a == 1) ? yp.x : z1[a].x;
-                        suA = (a == 0) ? urow_a<0>(cf, ca, am, c[a].x, ap, suA)
-                            : (a == 1) ? urow_a<1>(cf, ca, am, c[a].x, ap, suA)
-                                       : urow_a<2>(cf, ca, am, c[a].x, ap, suA);
-                    } else {
-                        ya = row7(czm, cym, cf.msx, dgA, cxpA, cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
-                    }
-                    if (cb) {
-                        const int sb = (cb >> (2 * a)) & 3;
-                        yb = (a == 0) ? cond_a<0>(mc, sb, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y, ub[0])
-                           : (a == 1) ? cond_a<1>(mc, sb, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y, ub[1])
-                                      : cond_a<2>(mc, sb, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y, ub[2]);
-                        const double am = (a == 0) ? c[a].x : (a == 1) ? ym.y : m[a].y;
-                        const double ap = (a == 0) ? xp : (a == 1) ? yp.y : z1[a].y;
-                        suB = (a == 0) ? urow_a<0>(cf, cb, am, c[a].y, ap, suB)
-                            : (a == 1) ? urow_a<1>(cf, cb, am, c[a].y, ap, suB)
-                                       : urow_a<2>(cf, cb, am, c[a].y, ap, suB);
-                    } else {
-                        yb = row7(czm, cym, cxmB, dgB, cf.msx, cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
-                    }
-                    pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
-                }
-                // U rows
-                double sa_ = 0.0, sb_ = 0.0;
-                if (ca) sa_ = urow_u(cf, ca, ua[2].m1, ua[1].m1, ua[0].m1, ugc.x, ua[0].p1, ua[1].p1, ua[2].p1, suA);
-                if (cb) sb_ = urow_u(cf, cb, ub[2].m1, ub[1].m1, ub[0].m1, ugc.y, ub[0].p1, ub[1].p1, ub[2].p1, suB);
-                pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1);
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { m[a] = c[a]; c[a] = z1[a]; }
-        ugm = ugc; ugc = ugp;
-        if (q >= 2) { pA += kdz; pU += G.ub_pl; }
-        __syncthreads();                                    // every thread is done with stage sp (load q-1)
-        if (tid == 0 && q >= 1 && q - 1 + NSTAGE < nload) issue(q - 1 + NSTAGE);
-        sp = s;
-        if (++s == NSTAGE) { s = 0; ph ^= 1u; }
-    }
     if (MODE != MODE_PLAIN) {
-        const int pidx = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        const int pidx = blockIdx.x;
         const unsigned ex = finalize_here ? expected : 0xffffffffu;
         if (MODE == MODE_AP)
             reduce_epilogue<1>(a0, 0.0, partials, pstride, pidx, ex, ctl.sc, RED_APR0, RED_APR0, sh);

@@ -3,16 +3,19 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eddy_currents_3d_b200 import lib, plate
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+only = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 3, 4]
 p = plate(N, "A")
 h = lib.Handle(p, device=0)
 n, nC = p.nCellsGlob, p.nCells
 names = ["spmv_Ap", "spmv_As", "s_update", "xr_update", "p_update"]
 byt = [24.0 * n + 5 * nC, 16.0 * n + 5 * nC, 24.0 * n, 56.0 * n, 32.0 * n]
 out = {}
-for w, (nm, b) in enumerate(zip(names, byt)):
+for w in only:
     ms = h.bench_kernel(w, 3, 20)
-    out[nm] = (round(ms, 4), round(b / ms / 1e6, 1))
+    out[names[w]] = (round(ms, 4), round(byt[w] / ms / 1e6, 1))
 tot = sum(v[0] for v in out.values())
-print(json.dumps({"N": N, "env": {k: v for k, v in os.environ.items() if k.startswith("EC3D_")}, "kernels(ms,GB/s)": out,
-                  "iter_ms": round(tot, 4), "iter_GBs": round((152.0 * n + 10 * nC) / tot / 1e6, 1)}))
+line = {"N": N, "env": {k: v for k, v in os.environ.items() if k.startswith("EC3D_")}, "kernels(ms,GB/s)": out}
+if len(only) == 5:
+    line.update({"iter_ms": round(tot, 4), "iter_GBs": round((152.0 * n + 10 * nC) / tot / 1e6, 1)})
+print(json.dumps(line))
 h.close()
