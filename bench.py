@@ -12,8 +12,8 @@ one NCCL halo exchange per SpMV and scalar all-reduces for the dot products).
   e2e                 : the same K steps through the C ABI with host buffers: per-step source
                         scalars H2D from pinned memory and the full Uaf/Jaf fields D2H into pinned
                         memory after every step (what the Fortran host needs for its VTK output).
-  roofline            : matrix-free SpMV (the dominant kernel pair k_air_spmv + k_cond_spmv fused
-                        with (As,s),(As,As)), algorithmic bytes 16 n + 5 nC over the
+  roofline            : matrix-free SpMV (k_spmv_tma, the TMA-staged stencil kernel fused with
+                        (As,s),(As,As)), algorithmic bytes 16 n + 5 nC over the
                         CUDA-event launch time measured here; peak from MEASURED_PEAKS.json.
   cpu_baseline        : the CPU oracle (oracle/, a port of the reference -- no Fortran compiler
                         exists here) timed on this host, 1 thread like the reference, on a bounded
@@ -173,7 +173,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=int(os.environ.get("EC3D_BENCH_GRID", "512")))
@@ -307,7 +307,7 @@ def main():
         "gpu_launches": int(c1["launches"] - c0["launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_air_spmv<AS>+k_cond_spmv<AS>",
+                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_spmv_tma<MODE_AS> (SpMV A*s fused with (As,s),(As,As))",
                      "algorithmic_bytes": bytes_spmv2, "ms_per_launch": ms_spmv2},
         "roofline_iteration": {"bound": "hbm", "achieved": it_bytes / (solve_ms_per_iter * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s",

@@ -10,6 +10,7 @@
 #include "ec3d_kernels.cuh"
 #include "ec3d_step.cuh"
 #include "ec3d_tma.cuh"
+#include "ec3d_p2p.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -145,9 +146,11 @@ struct Solver {
     int nblkVec = 1, vec = 1;
     // launches the SpMV kernel(s) for `mode`; returns kernels launched
     std::function<int(int mode, const VecSet &vs, const IterCtl &ctl)> spmv;
-    std::function<int(double *v)> halo;                 // refresh halo entries of v (nranks > 1)
+    std::function<int(double *v, int check_done)> halo; // refresh halo entries of v (nranks > 1)
     std::function<int(int slot, int count)> allreduce;  // sum sc->red[slot..slot+count) over ranks
     bool multi = false;
+    bool p2p = false;                                   // exchanges are plain kernels: graph capture allowed
+    bool x_halo_fresh = false;                          // the caller just exchanged the halo of X
     // graph of `graph_chunk` iterations (single rank only)
     cudaGraphExec_t graph = nullptr;
     int graph_chunk = 0;
@@ -164,7 +167,7 @@ static int solver_enqueue_iteration(Solver &s, int it_off)
     const SlabGeom &G = s.G;
     const IterCtl ctl{s.sc, s.iter_base, it_off};
     const unsigned nb = (unsigned)s.nblkVec;
-    if (s.multi) { int rc = s.halo(s.P); if (rc) return rc; }
+    if (s.multi) { int rc = s.halo(s.P, 1); if (rc) return rc; }
     {   // AP = A*P, (AP,R0)                                        solvers.f90:30-32
         VecSet vs{s.P, s.AP, s.R0, nullptr, nullptr, nullptr, nullptr};
         s.launches += s.spmv(MODE_AP, vs, ctl);
@@ -173,7 +176,7 @@ static int solver_enqueue_iteration(Solver &s, int it_off)
     if (s.vec == 2) k_s_update<2><<<nb, 256, 0, s.st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
     else            k_s_update<1><<<nb, 256, 0, s.st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
     LAUNCHED(s.launches);
-    if (s.multi) { int rc = s.allreduce(RED_SS, 1); if (rc) return rc; rc = s.halo(s.S); if (rc) return rc; }
+    if (s.multi) { int rc = s.allreduce(RED_SS, 1); if (rc) return rc; rc = s.halo(s.S, 1); if (rc) return rc; }
     {   // AS = A*S, (AS,S), (AS,AS)                                solvers.f90:39-40
         VecSet vs{s.S, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr};
         s.launches += s.spmv(MODE_AS, vs, ctl);
@@ -191,7 +194,7 @@ static int solver_enqueue_iteration(Solver &s, int it_off)
 
 static int solver_build_graph(Solver &s, int chunk)
 {
-    if (s.multi || chunk <= 0) return EC3D_OK;
+    if ((s.multi && !s.p2p) || chunk <= 0) return EC3D_OK;
     cudaGraph_t g = nullptr;
     const long long before = s.launches;
     const long long gbefore = g_launches.load();
@@ -213,7 +216,8 @@ static int solver_run(Solver &s, const double *B, double tol, int itmax, int *it
 {
     k_solver_reset<<<1, 1, 0, s.st>>>(s.sc, s.iter_base, tol, itmax);
     LAUNCHED(s.launches);
-    if (s.multi) { int rc = s.halo(s.X); if (rc) return rc; }
+    if (s.multi && !s.x_halo_fresh) { int rc = s.halo(s.X, 0); if (rc) return rc; }
+    s.x_halo_fresh = false;
     {   // R = B - A*X; R0 = R; P = R; ||b||^2; (R,R0)               solvers.f90:13-21
         VecSet vs{s.X, nullptr, nullptr, B, s.R, s.R0, s.P};
         const IterCtl ctl{s.sc, s.iter_base, 0};
@@ -448,6 +452,14 @@ struct ec3d_handle {
     // multi-GPU
     int nranks = 1, rank = 0;
     ncclComm_t comm = nullptr;
+    // peer-to-peer exchange over NVLink (ec3d_p2p.cuh); falls back to NCCL when CUDA IPC is unavailable
+    bool p2p = false;
+    PeerTable pt{};
+    CommBlock *d_cb = nullptr;
+    CommLocal *d_cl = nullptr;
+    void *ipc_vecs_lo = nullptr, *ipc_vecs_hi = nullptr;
+    void *ipc_cb[EC3D_MAX_RANKS] = {nullptr};
+    const double *halo_fresh = nullptr;      // vector whose halo was exchanged last and not modified since
     long long nU_send_lo = 0, nU_send_hi = 0;   // U entries in my first / last two planes
     // timing
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -456,11 +468,20 @@ struct ec3d_handle {
     long long launches = 0;
 };
 
-static int h_halo(ec3d_handle *h, double *v)
+static int h_halo(ec3d_handle *h, double *v, int check_done = 0)
 {
     if (h->nranks == 1) return EC3D_OK;
     const SlabGeom &G = h->G;
     const long long kdz = G.kdz;
+    if (h->p2p) {
+        const int vidx = (int)((v - h->vecs) / G.ltot);
+        const long long work = 3 * kdz / 2 + std::max(h->nU_send_lo, h->nU_send_hi);
+        const int nb = (int)std::max<long long>(1, std::min<long long>((work + 255) / 256, 148 * 4));
+        k_halo_push<<<nb, 256, 0, h->st>>>(G, h->pt, h->vecs, vidx, h->nU_send_lo, h->nU_send_hi, h->sol.sc, check_done, h->d_cl);
+        k_halo_wait<<<1, 32, 0, h->st>>>(h->pt, h->sol.sc, check_done, h->d_cl);
+        h->launches += 2; g_launches.fetch_add(2);
+        return EC3D_OK;
+    }
     NCCL_TRY(ncclGroupStart());
     if (h->rank > 0) {
         const int peer = h->rank - 1;
@@ -488,6 +509,11 @@ static int h_halo(ec3d_handle *h, double *v)
 static int h_allreduce(ec3d_handle *h, int slot, int count)
 {
     if (h->nranks == 1) return EC3D_OK;
+    if (h->p2p) {
+        k_reduce_xchg<<<1, 32, 0, h->st>>>(h->pt, h->sol.sc, slot, count, 0, h->d_cl);
+        h->launches += 1; g_launches.fetch_add(1);
+        return EC3D_OK;
+    }
     NCCL_TRY(ncclAllReduce(h->sol.sc->red + slot, h->sol.sc->red + slot, count, ncclDouble, ncclSum, h->comm, h->st));
     return EC3D_OK;
 }
@@ -568,6 +594,10 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     if (h->sol.graph) cudaGraphExecDestroy(h->sol.graph);
+    if (h->ipc_vecs_lo) cudaIpcCloseMemHandle(h->ipc_vecs_lo);
+    if (h->ipc_vecs_hi) cudaIpcCloseMemHandle(h->ipc_vecs_hi);
+    for (int r = 0; r < EC3D_MAX_RANKS; ++r) if (h->ipc_cb[r]) cudaIpcCloseMemHandle(h->ipc_cb[r]);
+    cudaFree(h->d_cb); cudaFree(h->d_cl);
     if (h->comm) ncclCommDestroy(h->comm);
     cudaFree(h->d_mc); cudaFree(h->d_geo); cudaFree(h->d_mat); cudaFree(h->d_cond_cells); cudaFree(h->d_flags);
     cudaFree(h->d_cls); cudaFree(h->d_ucompact); cudaFree(h->d_items);
@@ -580,6 +610,90 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
+    return EC3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// peer-to-peer exchange set-up: CUDA IPC mappings of the neighbours' vector allocations and of
+// every rank's CommBlock, agreed on by all ranks (any failure -> everybody stays on NCCL)
+// ------------------------------------------------------------------------------------------
+struct P2pXchg {
+    cudaIpcMemHandle_t hv, hc;
+    PeerGeom g;
+    int ok, pad;
+};
+
+static int all_ranks_agree(ec3d_handle *h, int *d_flag, int mine, bool *all_ok)
+{
+    CUDA_TRY(cudaMemcpyAsync(d_flag, &mine, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    NCCL_TRY(ncclAllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, h->comm, h->st));
+    int res = 0;
+    CUDA_TRY(cudaMemcpyAsync(&res, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    *all_ok = res != 0;
+    return EC3D_OK;
+}
+
+static int setup_p2p(ec3d_handle *h, bool want)
+{
+    const int nr = h->nranks, me = h->rank;
+    const SlabGeom &G = h->G;
+    CUDA_TRY(cudaMalloc(&h->d_cb, sizeof(CommBlock)));
+    CUDA_TRY(cudaMalloc(&h->d_cl, sizeof(CommLocal)));
+    CUDA_TRY(cudaMemset(h->d_cb, 0, sizeof(CommBlock)));
+    CUDA_TRY(cudaMemset(h->d_cl, 0, sizeof(CommLocal)));
+    P2pXchg mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = want ? 1 : 0;
+    if (want && (cudaIpcGetMemHandle(&mine.hv, h->vecs) != cudaSuccess || cudaIpcGetMemHandle(&mine.hc, h->d_cb) != cudaSuccess)) {
+        mine.ok = 0;
+        cudaGetLastError();
+    }
+    mine.g = PeerGeom{G.segA, G.offU, G.nUlo, G.nUown, G.ltot, G.nzl, 0};
+    P2pXchg *d_x = nullptr;
+    int *d_flag = nullptr;
+    CUDA_TRY(cudaMalloc(&d_x, (size_t)nr * sizeof(P2pXchg)));
+    CUDA_TRY(cudaMalloc(&d_flag, sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(d_x + me, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->st));
+    NCCL_TRY(ncclAllGather(d_x + me, d_x, sizeof(P2pXchg), ncclChar, h->comm, h->st));
+    std::vector<P2pXchg> all(nr);
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d_x, (size_t)nr * sizeof(P2pXchg), cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    int ok = 1;
+    for (int r = 0; r < nr; ++r) ok = ok && all[r].ok;
+    PeerTable &pt = h->pt;
+    memset(&pt, 0, sizeof(pt));
+    pt.nranks = nr; pt.rank = me;
+    if (ok) {
+        for (int r = 0; r < nr && ok; ++r) {
+            if (r == me) { pt.cb[r] = h->d_cb; continue; }
+            if (cudaIpcOpenMemHandle(&h->ipc_cb[r], all[r].hc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+            pt.cb[r] = (CommBlock *)h->ipc_cb[r];
+        }
+        if (ok && me > 0) {
+            if (cudaIpcOpenMemHandle(&h->ipc_vecs_lo, all[me - 1].hv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            pt.vecs_lo = (double *)h->ipc_vecs_lo; pt.g_lo = all[me - 1].g;
+        }
+        if (ok && me < nr - 1) {
+            if (cudaIpcOpenMemHandle(&h->ipc_vecs_hi, all[me + 1].hv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            pt.vecs_hi = (double *)h->ipc_vecs_hi; pt.g_hi = all[me + 1].g;
+        }
+    }
+    bool all_ok = false;
+    int rc = all_ranks_agree(h, d_flag, ok, &all_ok);     // also a barrier: every CommBlock is zeroed and mapped
+    cudaFree(d_x); cudaFree(d_flag);
+    if (rc) return rc;
+    h->p2p = all_ok;
+    if (!all_ok) {
+        if (h->ipc_vecs_lo) cudaIpcCloseMemHandle(h->ipc_vecs_lo);
+        if (h->ipc_vecs_hi) cudaIpcCloseMemHandle(h->ipc_vecs_hi);
+        for (int r = 0; r < nr; ++r) if (h->ipc_cb[r]) cudaIpcCloseMemHandle(h->ipc_cb[r]);
+        h->ipc_vecs_lo = h->ipc_vecs_hi = nullptr;
+        for (int r = 0; r < EC3D_MAX_RANKS; ++r) h->ipc_cb[r] = nullptr;
+        cudaGetLastError();
+    }
+    if (getenv("EC3D_VERBOSE") && me == 0)
+        fprintf(stderr, "ec3d: %d ranks, exchange over %s\n", nr, h->p2p ? "NVLink peer memory (CUDA IPC)" : "NCCL");
     return EC3D_OK;
 }
 
@@ -847,7 +961,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 2 * sizeof(double)));
     s.multi = h->nranks > 1;
     s.spmv = [h](int mode, const VecSet &vs, const IterCtl &ctl) { return h_spmv(h, mode, vs, ctl); };
-    s.halo = [h](double *v) { return h_halo(h, v); };
+    s.halo = [h](double *v, int check_done) { return h_halo(h, v, check_done); };
     s.allreduce = [h](int slot, int count) { return h_allreduce(h, slot, count); };
 
     // ---- validate conductor geometry, classify boundary-cell flags ----
@@ -1018,11 +1132,16 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         ncclUniqueId id;
         memcpy(&id, cfg->nccl_id, 128);
         NCCL_TRY(ncclCommInitRank(&h->comm, h->nranks, id, h->rank));
+        const char *ec = getenv("EC3D_COMM");
+        const bool want = !(ec && strcmp(ec, "nccl") == 0) && (kdz % 2 == 0) && h->nranks <= EC3D_MAX_RANKS;
+        int rc = setup_p2p(h, want);
+        if (rc) return rc;
+        s.p2p = h->p2p;
     }
     // ---- iteration graph (single rank) ----
     {
         const char *ge = getenv("EC3D_GRAPH");
-        if (h->nranks == 1 && (!ge || atoi(ge) != 0)) { int rc = solver_build_graph(s, 8); if (rc) return rc; }
+        if ((h->nranks == 1 || h->p2p) && (!ge || atoi(ge) != 0)) { int rc = solver_build_graph(s, 8); if (rc) return rc; }
     }
     CUDA_TRY(cudaStreamSynchronize(h->st));
     return EC3D_OK;
@@ -1071,6 +1190,10 @@ static int copy_in(ec3d_handle *h, double *dst_local, const double *src_global)
         CUDA_TRY(cudaMemcpyAsync(h->d_ucompact, src_global + h->u_glob0, (size_t)h->ncond * sizeof(double),
                                  cudaMemcpyHostToDevice, h->st));
         k_u_unpack<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(G, h->d_cond_cells, h->ncond, h->d_ucompact, dst_local);
+        LAUNCHED(h->launches);
+    }
+    if (h->p2p) {      // all ranks have finished reading their halos of earlier calls before anyone overwrites them
+        k_reduce_xchg<<<1, 32, 0, h->st>>>(h->pt, h->sol.sc, 0, 0, 1, h->d_cl);
         LAUNCHED(h->launches);
     }
     return h_halo(h, dst_local);
@@ -1199,6 +1322,7 @@ static int stage_rhs_pre(ec3d_handle *h)
     if (h->size_PHYS_C == 0) return EC3D_OK;
     int rc = h_halo(h, h->Uaf);      // the U-row right-hand side reads Az(k+-1) of Uaf
     if (rc) return rc;
+    h->sol.x_halo_fresh = (h->sol.X == h->Uaf);   // the solve's initial residual reuses it
     if (h->ncond) {
         k_rhs_pre<<<(h->ncond + 255) / 256, 256, 0, h->st>>>(h->G, h->cf, h->d_geo, h->d_cond_cells, h->ncond, h->d_flags, h->valdom,
                                                   h->Uaf, h->Jaf);
@@ -1215,6 +1339,11 @@ static int stage_solve(ec3d_handle *h, int32_t *iter)
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev[3], h->st));
     if (iter) *iter = it;
+    if (h->p2p) {
+        int err = 0;
+        CUDA_TRY(cudaMemcpy(&err, &h->d_cl->error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) { ec3d_set_error("peer-to-peer exchange timed out waiting for a neighbour"); return EC3D_ERR_NCCL; }
+    }
     return EC3D_OK;
 }
 

@@ -1,0 +1,72 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/multi_gpu_check.py [plate32|elmer|lim|plate64]
+
+Every rank owns a z-slab (NCCL halo exchange per SpMV, scalar all-reduces for the dots); after each
+timestep the owned field entries are summed over ranks into full vectors and compared on rank 0
+with the CPU oracle (test infrastructure) run on the same inputs.  Exit code 0 = parity holds."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from eddy_currents_3d_b200 import lib, plate, load_vxc  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "plate32"
+    nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(lib.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    nccl_id = bytes(idt.cpu().numpy().tobytes())
+    if what.startswith("plate"):
+        p = plate(int(what[5:]), "M")
+    else:
+        deck = {"elmer": "compare_to_Elmer", "lim": "LIM", "move": "ec_src_move_hole"}[what]
+        from eddy_currents_3d_b200.problem import load_problem_npz
+        p = load_problem_npz(os.path.join(ROOT, "tests", "golden", deck + ".npz"))
+    h = lib.Handle(p, nranks=world, rank=rank, nccl_id=nccl_id, device=local)
+    ref = None
+    if rank == 0:
+        from oracle import oracle
+        ref = oracle.OracleRun(p)
+    ok = True
+    T = 0.0
+    for s in range(nsteps):
+        f, v = p.source_scalars(T)
+        T = T + p.dt
+        dist.barrier()                              # rank 0 also runs the CPU oracle: enter the step together
+        it_g = h.step(f, v)
+        U, J = h.get_fields()                       # owned entries only, zeros elsewhere
+        tu, tj = torch.from_numpy(U).cuda(), torch.from_numpy(J).cuda()
+        dist.all_reduce(tu); dist.all_reduce(tj)
+        if rank == 0:
+            it_o = ref.step(f, v)
+            eu, ej = rel(tu.cpu().numpy(), ref.Uaf), rel(tj.cpu().numpy(), ref.Jaf)
+            print(f"[{what} x{world}] step {s}: iter gpu {it_g} oracle {it_o} relL2 U {eu:.2e} J {ej:.2e}", flush=True)
+            lim = 1e-9 if s == 0 else 1e-4
+            if abs(it_g - it_o) > max(1, int(np.ceil(0.05 * it_o))) or eu > lim or ej > lim:
+                ok = False
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    h.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
