@@ -68,7 +68,8 @@ __host__ __device__ __forceinline__ long long u_local(const SlabGeom &G, int i, 
 
 // Device-resident solver scalars (one per handle).
 struct Scal {
-    double red[8];                 // reduction results (all-reduced in place when nranks > 1)
+    double red[8];                 // reduction results (rounded; with several ranks: high words until the exchange)
+    double red_lo[8];              // low words of the per-rank double-double results (several ranks only)
     double rr0[2];                 // (R,R0), double-buffered by iteration parity
     double alpha, omega, beta;
     double bnorm;
@@ -79,7 +80,7 @@ struct Scal {
     int exit_kind;                 // 0 running, 1 ||s|| test, 2 ||r|| test, 3 iter>itmax, 4 ||b||==0
     int restarts;
     unsigned int counter;          // last-block ticket
-    int pad;
+    int multi;                     // != 0: several ranks, reductions stay double-double until the exchange
 };
 
 enum { RED_BB = 0, RED_RR_INIT = 1, RED_APR0 = 2, RED_SS = 3, RED_ASS = 4, RED_ASAS = 5, RED_RR = 6, RED_RR0N = 7 };

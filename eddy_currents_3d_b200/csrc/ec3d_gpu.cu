@@ -214,7 +214,7 @@ static int solver_build_graph(Solver &s, int chunk)
 // B is the right-hand side (local layout), s.X the initial guess / result.
 static int solver_run(Solver &s, const double *B, double tol, int itmax, int *iter)
 {
-    k_solver_reset<<<1, 1, 0, s.st>>>(s.sc, s.iter_base, tol, itmax);
+    k_solver_reset<<<1, 1, 0, s.st>>>(s.sc, s.iter_base, tol, itmax, s.multi ? 1 : 0);
     LAUNCHED(s.launches);
     if (s.multi && !s.x_halo_fresh) { int rc = s.halo(s.X, 0); if (rc) return rc; }
     s.x_halo_fresh = false;
@@ -340,7 +340,7 @@ static int csr_prepare(const double *valA, const int32_t *irow, const int32_t *j
     s.vec = (n % 2 == 0) ? 2 : 1;
     s.nblkVec = vec_blocks(n, s.vec);
     s.pstride = std::max(nblk, s.nblkVec);
-    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 4 * sizeof(double)));
     CUDA_TRY(cudaHostAlloc(&s.h_flags, 4 * sizeof(int), cudaHostAllocDefault));
     double *v = c.vecs;
     s.X = v; s.R = v + 2LL * n; s.R0 = v + 3LL * n; s.P = v + 4LL * n; s.AP = v + 5LL * n; s.S = v + 6LL * n;
@@ -457,6 +457,7 @@ struct ec3d_handle {
     PeerTable pt{};
     CommBlock *d_cb = nullptr;
     CommLocal *d_cl = nullptr;
+    double *d_gather = nullptr;              // NCCL path: [nranks][4] gathered double-double partials
     void *ipc_vecs_lo = nullptr, *ipc_vecs_hi = nullptr;
     void *ipc_cb[EC3D_MAX_RANKS] = {nullptr};
     const double *halo_fresh = nullptr;      // vector whose halo was exchanged last and not modified since
@@ -514,7 +515,11 @@ static int h_allreduce(ec3d_handle *h, int slot, int count)
         h->launches += 1; g_launches.fetch_add(1);
         return EC3D_OK;
     }
-    NCCL_TRY(ncclAllReduce(h->sol.sc->red + slot, h->sol.sc->red + slot, count, ncclDouble, ncclSum, h->comm, h->st));
+    // NCCL path: gather every rank's double-double partial(s), sum them in rank order on every rank
+    k_red_pack<<<1, 32, 0, h->st>>>(h->sol.sc, slot, count, h->d_gather + 4 * h->rank);
+    NCCL_TRY(ncclAllGather(h->d_gather + 4 * h->rank, h->d_gather, 4, ncclDouble, h->comm, h->st));
+    k_red_unpack<<<1, 32, 0, h->st>>>(h->sol.sc, slot, count, h->d_gather, h->nranks);
+    h->launches += 2; g_launches.fetch_add(2);
     return EC3D_OK;
 }
 
@@ -597,7 +602,7 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     if (h->ipc_vecs_lo) cudaIpcCloseMemHandle(h->ipc_vecs_lo);
     if (h->ipc_vecs_hi) cudaIpcCloseMemHandle(h->ipc_vecs_hi);
     for (int r = 0; r < EC3D_MAX_RANKS; ++r) if (h->ipc_cb[r]) cudaIpcCloseMemHandle(h->ipc_cb[r]);
-    cudaFree(h->d_cb); cudaFree(h->d_cl);
+    cudaFree(h->d_cb); cudaFree(h->d_cl); cudaFree(h->d_gather);
     if (h->comm) ncclCommDestroy(h->comm);
     cudaFree(h->d_mc); cudaFree(h->d_geo); cudaFree(h->d_mat); cudaFree(h->d_cond_cells); cudaFree(h->d_flags);
     cudaFree(h->d_cls); cudaFree(h->d_ucompact); cudaFree(h->d_items);
@@ -640,6 +645,7 @@ static int setup_p2p(ec3d_handle *h, bool want)
     const SlabGeom &G = h->G;
     CUDA_TRY(cudaMalloc(&h->d_cb, sizeof(CommBlock)));
     CUDA_TRY(cudaMalloc(&h->d_cl, sizeof(CommLocal)));
+    CUDA_TRY(cudaMalloc(&h->d_gather, (size_t)nr * 4 * sizeof(double)));
     CUDA_TRY(cudaMemset(h->d_cb, 0, sizeof(CommBlock)));
     CUDA_TRY(cudaMemset(h->d_cl, 0, sizeof(CommLocal)));
     P2pXchg mine;
@@ -958,7 +964,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         h->nblkCond = (h->ncond + 255) / 256;
     }
     s.pstride = std::max(h->nblkAir + h->nblkCond, s.nblkVec) + 8;
-    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 4 * sizeof(double)));
     s.multi = h->nranks > 1;
     s.spmv = [h](int mode, const VecSet &vs, const IterCtl &ctl) { return h_spmv(h, mode, vs, ctl); };
     s.halo = [h](double *v, int check_done) { return h_halo(h, v, check_done); };
@@ -1076,7 +1082,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         if (h->nblkAir + 8 > s.pstride) {
             cudaFree(s.partials);
             s.pstride = h->nblkAir + 8;
-            CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 2 * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 4 * sizeof(double)));
         }
     }
     // ---- sources ----

@@ -4,10 +4,13 @@
 // Arithmetic: fp64 with explicit round-to-nearest mul/add (__dmul_rn/__dadd_rn are never
 // contracted into FMA), each row summed in ascending column order starting from 0 -- the order of
 // the reference's sprsAx (solvers.f90:54-61) -- so the matrix-free operator is bit-identical to a
-// sequential CSR row sum.  Dot products use a fixed reduction tree (thread-sequential, warp
-// butterfly, warp-0 across warps, last block over the per-block partials in index order), hence
-// results are reproducible run to run; they differ from the reference's sequential dot_product
-// only by summation order.
+// sequential CSR row sum.  Dot products: the products are formed per element / per cell pair in a
+// fixed order that does not depend on how the grid is cut into slabs, chunks or blocks, and
+// everything above that level (per thread across planes, warp, block, blocks, ranks) is summed in
+// double-double (error-free TwoSum), whose result rounded to fp64 is the same for any summation
+// order (up to ties at the 1e-32 level).  So the solver scalars -- and with them iteration counts
+// and fields -- are reproducible run to run AND identical for 1, 2, 4, 8 GPUs; they differ from the
+// reference's sequential dot_product only by the reference's own rounding error.
 #pragma once
 #include "ec3d_common.cuh"
 #include "ec3d_rows.cuh"
@@ -27,64 +30,98 @@ struct VecSet {
 };
 
 // --------------------------------------------------------------------------------------------
-// reductions
+// reductions (double-double)
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v)
+struct dd {
+    double hi, lo;
+};
+__device__ __forceinline__ dd dd_zero() { return dd{0.0, 0.0}; }
+
+// a += b, b a double: hi + b is split exactly into the rounded sum and its error (Knuth TwoSum)
+__device__ __forceinline__ void dd_add_d(dd &a, const double b)
+{
+    const double s = DADD(a.hi, b);
+    const double bb = DSUB(s, a.hi);
+    const double e = DADD(DSUB(a.hi, DSUB(s, bb)), DSUB(b, bb));
+    a.hi = s;
+    a.lo = DADD(a.lo, e);
+}
+// a += b, both double-double
+__device__ __forceinline__ void dd_add_dd(dd &a, const dd b)
+{
+    dd_add_d(a, b.hi);
+    a.lo = DADD(a.lo, b.lo);
+}
+__device__ __forceinline__ double dd_round(const dd a) { return DADD(a.hi, a.lo); }
+
+__device__ __forceinline__ dd warp_sum(dd v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = DADD(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        dd w;
+        w.hi = __shfl_xor_sync(0xffffffffu, v.hi, o);
+        w.lo = __shfl_xor_sync(0xffffffffu, v.lo, o);
+        dd_add_dd(v, w);
+    }
     return v;
 }
 
 // Sum over the block; result valid in thread 0.  blockDim.x*blockDim.y*blockDim.z <= 1024.
-__device__ __forceinline__ double block_sum(double v, double *sh /* >= 32 doubles */)
+__device__ __forceinline__ dd block_sum(dd v, double *sh /* >= 64 doubles */)
 {
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     const int nthr = blockDim.x * blockDim.y * blockDim.z;
     const int lane = tid & 31, w = tid >> 5, nw = (nthr + 31) >> 5;
     v = warp_sum(v);
     __syncthreads();
-    if (lane == 0) sh[w] = v;
+    if (lane == 0) { sh[2 * w] = v.hi; sh[2 * w + 1] = v.lo; }
     __syncthreads();
-    double r = 0.0;
+    dd r = dd_zero();
     if (tid == 0) {
-        for (int q = 0; q < nw; ++q) r = DADD(r, sh[q]);
+        for (int q = 0; q < nw; ++q) dd_add_dd(r, dd{sh[2 * q], sh[2 * q + 1]});
     }
     return r;
 }
 
 // Stores this block's partial(s); the last block of the GROUP of kernels that share `sc->counter`
 // (expected = total number of blocks that will call this with the same partials array) sums all
-// partials in index order and writes sc->red[slot0], sc->red[slot1].
+// partials and writes sc->red[slot0], sc->red[slot1] (rounded; with several ranks the unrounded
+// double-double goes to red / red_lo and the cross-rank exchange rounds after summing the ranks).
+// partials: 4 * pstride doubles.
 template <int NRED>
-__device__ __forceinline__ void reduce_epilogue(double a0, double a1, double *partials, int pstride, int pidx,
+__device__ __forceinline__ void reduce_epilogue(dd a0, dd a1, double *partials, int pstride, int pidx,
                                                 unsigned expected, Scal *sc, int slot0, int slot1, double *sh)
 {
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     const int nthr = blockDim.x * blockDim.y * blockDim.z;
-    double s0 = block_sum(a0, sh);
-    double s1 = 0.0;
+    dd s0 = block_sum(a0, sh);
+    dd s1 = dd_zero();
     if (NRED > 1) s1 = block_sum(a1, sh);
     __shared__ unsigned ticket_s;
     if (tid == 0) {
-        partials[pidx] = s0;
-        if (NRED > 1) partials[pstride + pidx] = s1;
+        partials[2 * pidx] = s0.hi; partials[2 * pidx + 1] = s0.lo;
+        if (NRED > 1) { partials[2 * (pstride + pidx)] = s1.hi; partials[2 * (pstride + pidx) + 1] = s1.lo; }
         __threadfence();
         ticket_s = atomicAdd(&sc->counter, 1u);
     }
     __syncthreads();
     if (ticket_s != expected - 1) return;
     __threadfence();
-    double t0 = 0.0, t1 = 0.0;
+    dd t0 = dd_zero(), t1 = dd_zero();
     for (unsigned q = tid; q < expected; q += nthr) {
-        t0 = DADD(t0, __ldcg(partials + q));
-        if (NRED > 1) t1 = DADD(t1, __ldcg(partials + pstride + q));
+        dd_add_dd(t0, dd{__ldcg(partials + 2 * q), __ldcg(partials + 2 * q + 1)});
+        if (NRED > 1) dd_add_dd(t1, dd{__ldcg(partials + 2 * (pstride + q)), __ldcg(partials + 2 * (pstride + q) + 1)});
     }
     t0 = block_sum(t0, sh);
     if (NRED > 1) t1 = block_sum(t1, sh);
     if (tid == 0) {
-        sc->red[slot0] = t0;
-        if (NRED > 1) sc->red[slot1] = t1;
+        if (sc->multi) {
+            sc->red[slot0] = t0.hi; sc->red_lo[slot0] = t0.lo;
+            if (NRED > 1) { sc->red[slot1] = t1.hi; sc->red_lo[slot1] = t1.lo; }
+        } else {
+            sc->red[slot0] = dd_round(t0);
+            if (NRED > 1) sc->red[slot1] = dd_round(t1);
+        }
         sc->counter = 0u;
         __threadfence();
     }
@@ -174,7 +211,7 @@ __global__ void __launch_bounds__(TX *TY)
 k_air_spmv(const SlabGeom G, const Coef cf, const int *__restrict__ geo, const VecSet vs, const IterCtl ctl,
            const int zc, double *partials, const int pstride, const unsigned expected, const int finalize_here)
 {
-    __shared__ double sh[32];
+    __shared__ double sh[64];
     if (!spmv_guard<MODE>(ctl)) return;
     const int i = blockIdx.x * TX + threadIdx.x, j = blockIdx.y * TY + threadIdx.y;
     const int kb = G.k0 + blockIdx.z * zc;
@@ -229,13 +266,13 @@ k_air_spmv(const SlabGeom G, const Coef cf, const int *__restrict__ geo, const V
         const int pidx = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         // INIT reduces (bb, rr), AS reduces (ass, asas), AP reduces (apr0)
         if (MODE == MODE_AP)
-            reduce_epilogue<1>(a0, 0.0, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
+            reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
                                RED_APR0, RED_APR0, sh);
         else if (MODE == MODE_AS)
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
                                RED_ASS, RED_ASAS, sh);
         else
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
                                RED_BB, RED_RR_INIT, sh);
     }
 }
@@ -301,7 +338,7 @@ k_cond_spmv(const SlabGeom G, const Coef cf, const MatCoef *__restrict__ mcs, co
             const VecSet vs, const IterCtl ctl, double *partials, const int pstride, const int pbase,
             const unsigned expected)
 {
-    __shared__ double sh[32];
+    __shared__ double sh[64];
     if (!spmv_guard<MODE>(ctl)) return;
     double a0 = 0.0, a1 = 0.0;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,11 +365,11 @@ k_cond_spmv(const SlabGeom G, const Coef cf, const MatCoef *__restrict__ mcs, co
     if (MODE != MODE_PLAIN) {
         const int pidx = pbase + blockIdx.x;
         if (MODE == MODE_AP)
-            reduce_epilogue<1>(a0, 0.0, partials, pstride, pidx, expected, ctl.sc, RED_APR0, RED_APR0, sh);
+            reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_APR0, RED_APR0, sh);
         else if (MODE == MODE_AS)
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, sh);
         else
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, expected, ctl.sc, RED_BB, RED_RR_INIT, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, pidx, expected, ctl.sc, RED_BB, RED_RR_INIT, sh);
     }
 }
 
@@ -345,7 +382,7 @@ __global__ void __launch_bounds__(256)
 k_csr_spmv(const int n, const int *__restrict__ irow, const int *__restrict__ jcol, const double *__restrict__ valA,
            const VecSet vs, const IterCtl ctl, double *partials, const int pstride, const unsigned expected)
 {
-    __shared__ double sh[32];
+    __shared__ double sh[64];
     if (!spmv_guard<MODE>(ctl)) return;
     double a0 = 0.0, a1 = 0.0;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,11 +394,11 @@ k_csr_spmv(const int n, const int *__restrict__ irow, const int *__restrict__ jc
     }
     if (MODE != MODE_PLAIN) {
         if (MODE == MODE_AP)
-            reduce_epilogue<1>(a0, 0.0, partials, pstride, blockIdx.x, expected, ctl.sc, RED_APR0, RED_APR0, sh);
+            reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), partials, pstride, blockIdx.x, expected, ctl.sc, RED_APR0, RED_APR0, sh);
         else if (MODE == MODE_AS)
-            reduce_epilogue<2>(a0, a1, partials, pstride, blockIdx.x, expected, ctl.sc, RED_ASS, RED_ASAS, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, blockIdx.x, expected, ctl.sc, RED_ASS, RED_ASAS, sh);
         else
-            reduce_epilogue<2>(a0, a1, partials, pstride, blockIdx.x, expected, ctl.sc, RED_BB, RED_RR_INIT, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, blockIdx.x, expected, ctl.sc, RED_BB, RED_RR_INIT, sh);
     }
 }
 
@@ -380,14 +417,14 @@ __global__ void __launch_bounds__(256)
 k_s_update(const SlabGeom G, const double *__restrict__ R, const double *__restrict__ AP, double *__restrict__ S,
            const IterCtl ctl, double *partials, const int pstride, const unsigned expected)
 {
-    __shared__ double sh[32];
+    __shared__ double sh[64];
     Scal *sc = ctl.sc;
     if (sc->done) return;
     const int it = *ctl.iter_base + ctl.it_off;
     const double rr0 = (it == 1) ? sc->red[RED_RR_INIT] : sc->rr0[it & 1];
     const double alpha = rr0 / sc->red[RED_APR0];
     if (is_block0()) sc->alpha = alpha;
-    double acc = 0.0;
+    dd acc = dd_zero();
     const long long units = G.n_own / VEC;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < units;
          q += (long long)gridDim.x * blockDim.x) {
@@ -399,15 +436,14 @@ k_s_update(const SlabGeom G, const double *__restrict__ R, const double *__restr
             s.x = DSUB(r.x, DMUL(alpha, ap.x));
             s.y = DSUB(r.y, DMUL(alpha, ap.y));
             *reinterpret_cast<double2 *>(S + l) = s;
-            acc = DADD(acc, DMUL(s.x, s.x));
-            acc = DADD(acc, DMUL(s.y, s.y));
+            dd_add_d(acc, __fma_rn(s.y, s.y, DMUL(s.x, s.x)));      // pair sum: fixed, partition independent
         } else {
             const double s = DSUB(R[l], DMUL(alpha, AP[l]));
             S[l] = s;
-            acc = DADD(acc, DMUL(s, s));
+            dd_add_d(acc, DMUL(s, s));
         }
     }
-    reduce_epilogue<1>(acc, 0.0, partials, pstride, blockIdx.x, expected, sc, RED_SS, RED_SS, sh);
+    reduce_epilogue<1>(acc, dd_zero(), partials, pstride, blockIdx.x, expected, sc, RED_SS, RED_SS, sh);
 }
 
 // K5: if ||S|| converged: X = X + alpha*P (solvers.f90:36).  Else omega = (AS,S)/(AS,AS);
@@ -418,7 +454,7 @@ k_xr_update(const SlabGeom G, double *__restrict__ X, const double *__restrict__
             const double *__restrict__ AS, double *__restrict__ R, const double *__restrict__ R0,
             const IterCtl ctl, double *partials, const int pstride, const unsigned expected)
 {
-    __shared__ double sh[32];
+    __shared__ double sh[64];
     Scal *sc = ctl.sc;
     if (sc->done) return;
     const double alpha = sc->alpha;
@@ -435,7 +471,7 @@ k_xr_update(const SlabGeom G, double *__restrict__ X, const double *__restrict__
     }
     const double omega = sc->red[RED_ASS] / sc->red[RED_ASAS];
     if (is_block0()) sc->omega = omega;
-    double a0 = 0.0, a1 = 0.0;
+    dd a0 = dd_zero(), a1 = dd_zero();
     for (long long q = q0; q < units; q += qs) {
         const long long l = own_to_local(G, q * VEC);
         if (VEC == 2) {
@@ -451,15 +487,15 @@ k_xr_update(const SlabGeom G, double *__restrict__ X, const double *__restrict__
             r.y = DSUB(s.y, DMUL(omega, as.y));
             *reinterpret_cast<double2 *>(X + l) = x;
             *reinterpret_cast<double2 *>(R + l) = r;
-            a0 = DADD(a0, DMUL(r.x, r.x)); a0 = DADD(a0, DMUL(r.y, r.y));
-            a1 = DADD(a1, DMUL(r.x, r0.x)); a1 = DADD(a1, DMUL(r.y, r0.y));
+            dd_add_d(a0, __fma_rn(r.y, r.y, DMUL(r.x, r.x)));
+            dd_add_d(a1, __fma_rn(r.y, r0.y, DMUL(r.x, r0.x)));
         } else {
             const double s = S[l];
             X[l] = DADD(DADD(X[l], DMUL(alpha, P[l])), DMUL(omega, s));
             const double r = DSUB(s, DMUL(omega, AS[l]));
             R[l] = r;
-            a0 = DADD(a0, DMUL(r, r));
-            a1 = DADD(a1, DMUL(r, R0[l]));
+            dd_add_d(a0, DMUL(r, r));
+            dd_add_d(a1, DMUL(r, R0[l]));
         }
     }
     reduce_epilogue<2>(a0, a1, partials, pstride, blockIdx.x, expected, sc, RED_RR, RED_RR0N, sh);
@@ -511,9 +547,10 @@ k_p_update(const SlabGeom G, double *__restrict__ P, const double *__restrict__ 
     }
 }
 
-__global__ void k_solver_reset(Scal *sc, int *iter_base, double tol, int itmax)
+__global__ void k_solver_reset(Scal *sc, int *iter_base, double tol, int itmax, int multi)
 {
-    for (int q = 0; q < 8; ++q) sc->red[q] = 0.0;
+    for (int q = 0; q < 8; ++q) { sc->red[q] = 0.0; sc->red_lo[q] = 0.0; }
+    sc->multi = multi;
     sc->rr0[0] = sc->rr0[1] = 0.0;
     sc->alpha = sc->omega = sc->beta = 0.0;
     sc->tol = tol; sc->itmax = itmax;
@@ -522,6 +559,25 @@ __global__ void k_solver_reset(Scal *sc, int *iter_base, double tol, int itmax)
 }
 
 __global__ void k_iter_advance(int *iter_base, int by) { *iter_base += by; }
+
+// NCCL path of the cross-rank reduction: (hi, lo) of up to two results <-> gather buffer
+__global__ void k_red_pack(const Scal *sc, int slot, int count, double *mine /* 4 doubles */)
+{
+    if (threadIdx.x != 0) return;
+    for (int q = 0; q < 2; ++q) {
+        mine[2 * q] = q < count ? sc->red[slot + q] : 0.0;
+        mine[2 * q + 1] = q < count ? sc->red_lo[slot + q] : 0.0;
+    }
+}
+__global__ void k_red_unpack(Scal *sc, int slot, int count, const double *all /* [nranks][4] */, int nranks)
+{
+    if (threadIdx.x != 0) return;
+    for (int q = 0; q < count; ++q) {
+        dd t = dd_zero();
+        for (int r = 0; r < nranks; ++r) dd_add_dd(t, dd{all[4 * r + 2 * q], all[4 * r + 2 * q + 1]});
+        sc->red[slot + q] = dd_round(t);
+    }
+}
 
 // generic helpers
 __global__ void k_fill(double *p, long long n, double v)

@@ -11,7 +11,8 @@
 //   k_halo_wait   one thread waits until both neighbours' flags reached this rank's epoch
 //   k_reduce_xchg stores this rank's partial result(s) into every rank's CommBlock (slot chosen by
 //                 epoch parity), raises the flags, waits for all contributions and sums them in
-//                 rank order -- bit-identical on every rank, so all ranks take the same branches
+//                 rank order in double-double -- bit-identical on every rank (all ranks take the
+//                 same branches) and, rounded, the same value a single GPU computes
 //
 // All epochs live in device memory and are advanced by the kernels themselves, so a whole chunk
 // of iterations (compute + exchange) is one CUDA graph.  Two pushes into the same halo slot are
@@ -20,13 +21,14 @@
 // ~30 s and set CommLocal::error instead of hanging the GPU.
 #pragma once
 #include "ec3d_common.cuh"
+#include "ec3d_kernels.cuh"
 
 #define EC3D_MAX_RANKS 16
 
 struct CommBlock {                                   // written by peers
     unsigned long long halo_flag[2];                 // [0] from rank-1, [1] from rank+1: epoch of their last push
     unsigned long long red_flag[EC3D_MAX_RANKS];     // epoch of rank r's last contribution
-    double red_val[2][EC3D_MAX_RANKS][2];            // [epoch parity][rank][value]
+    double red_val[2][EC3D_MAX_RANKS][4];            // [epoch parity][rank][hi0, lo0, hi1, lo1]
 };
 
 struct CommLocal {                                   // this rank only
@@ -145,7 +147,10 @@ __global__ void k_reduce_xchg(const PeerTable pt, Scal *sc, const int slot, cons
     const int par = (int)(e & 1ull);
     if (lane < pt.nranks) {
         CommBlock *dst = pt.cb[lane];
-        for (int q = 0; q < count; ++q) dst->red_val[par][pt.rank][q] = sc->red[slot + q];
+        for (int q = 0; q < count; ++q) {
+            dst->red_val[par][pt.rank][2 * q] = sc->red[slot + q];
+            dst->red_val[par][pt.rank][2 * q + 1] = sc->red_lo[slot + q];
+        }
         __threadfence_system();
         st_release_sys(&dst->red_flag[pt.rank], e);
     }
@@ -156,9 +161,10 @@ __global__ void k_reduce_xchg(const PeerTable pt, Scal *sc, const int slot, cons
     if (lane == 0) {
         if (!ok) cl->error = 1;
         for (int q = 0; q < count; ++q) {
-            double s = 0.0;
-            for (int r = 0; r < pt.nranks; ++r) s = __dadd_rn(s, *(volatile double *)&me->red_val[par][r][q]);
-            sc->red[slot + q] = s;
+            dd t = dd_zero();                        // double-double sum in rank order, rounded once
+            for (int r = 0; r < pt.nranks; ++r)
+                dd_add_dd(t, dd{*(volatile double *)&me->red_val[par][r][2 * q], *(volatile double *)&me->red_val[par][r][2 * q + 1]});
+            sc->red[slot + q] = dd_round(t);
         }
     }
 }

@@ -275,7 +275,7 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
                                                const CUtensorMap &tmAuxA, const CUtensorMap &tmAuxU, const SlabGeom &G,
                                                const Coef &cf, const MatCoef &mc, const VecSet &vs, const TmaCtx &t,
                                                unsigned char *smem, unsigned long long *full, unsigned *cnt,
-                                               double &a0, double &a1)
+                                               dd &acc0, dd &acc1)
 {
     using namespace tma;
     constexpr bool HAS_AUX = (MODE == MODE_AP || MODE == MODE_INIT);
@@ -358,6 +358,9 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
                     if (HAS_U && t.inUxy && k >= G.ub_k0 && k < ukB) auxU = ld2(auxp + pU);
                 }
                 const int sprev = (s == 0) ? NSTAGE - 1 : s - 1;
+                // this thread's dot-product terms of plane k: summed in a fixed order here, accumulated
+                // across planes in double-double (independent of how z is cut into items and slabs)
+                double a0 = 0.0, a1 = 0.0;
                 own_pair(sz_, q);
                 if (t.active) {
                     const unsigned char *stp = smem + sprev * STAGE_BYTES;
@@ -499,6 +502,10 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
                         pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1);
                     }
                 }
+                if (MODE != MODE_PLAIN) {
+                    dd_add_d(acc0, a0);
+                    if (MODE != MODE_AP) dd_add_d(acc1, a1);
+                }
                 pA += kdz; pU += G.ub_pl;
                 release(q - 1);
                 advance();
@@ -517,7 +524,7 @@ k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 {
     using namespace tma;
     extern __shared__ unsigned char smem_raw[];
-    __shared__ double sh[32];
+    __shared__ double sh[64];
     __shared__ __align__(8) unsigned long long full[NSTAGE];
     __shared__ unsigned cnt[NSTAGE];
     if (!spmv_guard<MODE>(ctl)) return;
@@ -548,7 +555,7 @@ k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
     __syncthreads();
 
-    double a0 = 0.0, a1 = 0.0;
+    dd a0 = dd_zero(), a1 = dd_zero();
     if ((DBG & 16) && !w.has_u) return;                  // timing experiment: heavy items only
     if (w.has_u && !(DBG & 8)) tma_plane_loop<MODE, NSTAGE, true, DBG>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
     else if (!((DBG & 32) && w.has_u)) tma_plane_loop<MODE, NSTAGE, false, DBG>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
@@ -557,7 +564,7 @@ k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         const int pidx = blockIdx.x;
         const unsigned ex = finalize_here ? expected : 0xffffffffu;
         if (MODE == MODE_AP)
-            reduce_epilogue<1>(a0, 0.0, partials, pstride, pidx, ex, ctl.sc, RED_APR0, RED_APR0, sh);
+            reduce_epilogue<1>(a0, dd_zero(), partials, pstride, pidx, ex, ctl.sc, RED_APR0, RED_APR0, sh);
         else if (MODE == MODE_AS)
             reduce_epilogue<2>(a0, a1, partials, pstride, pidx, ex, ctl.sc, RED_ASS, RED_ASAS, sh);
         else
