@@ -862,6 +862,13 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     segA += segA & 1;
     G.segA = segA; G.offU = 3 * segA;
     G.ltot = G.offU + G.nUlo + G.nUown + G.nUhi + 2;
+    {
+        // vectors are laid out back to back; an odd multiple of 4 KiB between them keeps the 5-7 streams
+        // of a BLAS-1 kernel from sitting at the same offset of a DRAM page / bank (EC3D_VPAD overrides)
+        const char *ep = getenv("EC3D_VPAD");
+        const long long pad = ep ? atoll(ep) : 0;
+        G.ltot += pad;
+    }
     G.ltot += G.ltot & 1;
     for (int c = 0; c < 3; ++c) {
         G.own_off[c] = c * segA + kdz; G.own_len[c] = (long long)G.nzl * kdz;
@@ -1012,65 +1019,64 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         if (rc) return rc;
         // work list: (tile column, z range) items.  Tile columns that touch the conductor's bounding
         // box are split at the box's first / last plane so that items are either free of conductor
-        // cells (lean 7-point loop) or carry them (U tiles, class bytes, conductor rows).  Each range is
-        // cut into equal chunks of at most zc planes (zc/2 for ranges with conductor cells, which cost
-        // about twice as much per plane).  An item loads 2 planes more than it computes and pays one
-        // pipeline fill, so long chunks are cheaper -- but CTAs are latency bound, the hardware hands
-        // items out in blockIdx order to 2 x 148 CTA slots, and the last round must not be half empty.
-        // zc is therefore chosen by simulating that list schedule with a simple cost model.
+        // cells (lean 7-point loop) or carry them (U tiles, class bytes, conductor rows; about twice the
+        // cost per plane, hence half the length).  An item loads 2 planes more than it computes.
         const int tx = (sdx + tma::TX - 1) / tma::TX, ty = (sdy + tma::TY - 1) / tma::TY;
         const int ck0 = std::max(G.k0, G.ub_k0), ck1 = std::min(G.k1, G.ub_k0 + G.ub_nz);   // conductor planes of this slab
+        const char *eo = getenv("EC3D_ORDER");
+        const bool plane_major = !(eo && atoi(eo) == 0);
         auto build_items = [&](int zc, std::vector<WorkItem> &items) {
+            // cuts on a GLOBAL z grid (multiples of zc; zc/2 inside the conductor's z range) so that the
+            // items of neighbouring tile columns cover the same planes and march in lock step
             std::vector<WorkItem> light;
             items.clear();
+            const int zh = std::max(2, zc / 2);
+            std::vector<int> cuts;
             for (int by = 0; by < ty; ++by)
                 for (int bx = 0; bx < tx; ++bx) {
                     const int x0 = bx * tma::TX, y0 = by * tma::TY;
                     const bool touch = G.ub_nz > 0 && ck1 > ck0 && x0 < G.ub_i0 + G.ub_nx && x0 + tma::TX > G.ub_i0 &&
                                        y0 < G.ub_j0 + G.ub_ny && y0 + tma::TY > G.ub_j0;
-                    const int cuts[4] = {G.k0, touch ? ck0 : G.k1, touch ? ck1 : G.k1, G.k1};
-                    for (int r = 0; r < 3; ++r) {
-                        const int ra = cuts[r], rb = cuts[r + 1];
-                        if (rb <= ra) continue;
-                        const int has_u = (touch && r == 1) ? 1 : 0;
-                        const int zmax = has_u ? std::max(4, zc / 2) : zc;
-                        const int nch = (rb - ra + zmax - 1) / zmax, len = (rb - ra + nch - 1) / nch;
-                        for (int ka = ra; ka < rb; ka += len)
-                            (has_u ? items : light).push_back(WorkItem{x0, y0, ka, std::min(ka + len, rb), has_u, 0, 0, 0});
+                    cuts.clear();
+                    cuts.push_back(G.k0); cuts.push_back(G.k1);
+                    for (int k = (G.k0 / zc + 1) * zc; k < G.k1; k += zc) cuts.push_back(k);
+                    if (touch) {
+                        cuts.push_back(ck0); cuts.push_back(ck1);
+                        for (int k = (ck0 / zh + 1) * zh; k < ck1; k += zh) cuts.push_back(k);
                     }
+                    std::sort(cuts.begin(), cuts.end());
+                    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+                    // segments; short ones are merged into the previous segment of the same kind
+                    std::vector<WorkItem> col;
+                    for (size_t q = 0; q + 1 < cuts.size(); ++q) {
+                        const int ka = cuts[q], kb_ = cuts[q + 1];
+                        const int has_u = (touch && ka >= ck0 && kb_ <= ck1) ? 1 : 0;
+                        const int minlen = std::max(2, (has_u ? zh : zc) / 4);
+                        if (!col.empty() && col.back().has_u == has_u && (kb_ - ka < minlen || col.back().ke - col.back().kb < minlen))
+                            col.back().ke = kb_;
+                        else
+                            col.push_back(WorkItem{x0, y0, ka, kb_, has_u, 0, 0, 0});
+                    }
+                    for (const WorkItem &w : col) (w.has_u ? items : light).push_back(w);
                 }
-            items.insert(items.end(), light.begin(), light.end());   // items with conductor cells are scheduled first
+            items.insert(items.end(), light.begin(), light.end());   // items with conductor cells first ...
+            // ... then plane-major: CTAs that run at the same time work on neighbouring tiles of the same
+            // z range at the same z phase, so the y-halo rows a tile shares with its neighbours (2 of 10
+            // rows per box) are still in L2 when the neighbour asks for them (at 512^3 a column-major
+            // order re-reads them from HBM: +27 % DRAM reads)
+            if (plane_major)
+                std::stable_sort(items.begin(), items.end(), [](const WorkItem &a, const WorkItem &b) { return a.kb < b.kb; });
         };
-        auto makespan = [&](const std::vector<WorkItem> &items) {
-            const int slots = 2 * 148;
-            std::vector<double> freeat(slots, 0.0);        // min-heap by hand: slots is small
-            std::make_heap(freeat.begin(), freeat.end(), std::greater<double>());
-            double end = 0.0;
-            for (const WorkItem &w : items) {
-                std::pop_heap(freeat.begin(), freeat.end(), std::greater<double>());
-                const double cost = 2.5 + (w.ke - w.kb) * (w.has_u ? 2.5 : 1.0) + 2.0 * 0.35;   // fill + planes + 2 halo loads
-                freeat.back() += cost;
-                end = std::max(end, freeat.back());
-                std::push_heap(freeat.begin(), freeat.end(), std::greater<double>());
-            }
-            return end;
-        };
-        std::vector<WorkItem> items, cand;
-        int zc = 0;
+        // zc: measured on plate(256) / plate(512), 32..48 planes per item is the flat optimum (longer items
+        // leave too few CTAs for the last round, shorter ones pay the 2 extra planes and the pipeline fill
+        // more often); small grids get shorter items so that every SM has work
+        std::vector<WorkItem> items;
+        int zc = (int)std::min<long long>(48, std::max<long long>(4, (long long)G.nzl * tx * ty / (2 * 148)));
         {
             const char *ez = getenv("EC3D_ZC");
-            if (ez && atoi(ez) > 0) {
-                zc = atoi(ez);
-                build_items(zc, items);
-            } else {
-                double best = 0.0;
-                for (int z = std::min(8, G.nzl); z <= std::min(96, G.nzl); ++z) {
-                    build_items(z, cand);
-                    const double t = makespan(cand);
-                    if (zc == 0 || t < best * 0.995) { best = t; zc = z; items.swap(cand); }
-                }
-            }
+            if (ez && atoi(ez) > 0) zc = atoi(ez);
         }
+        build_items(zc, items);
         h->zc = zc;
         if (getenv("EC3D_VERBOSE")) fprintf(stderr, "ec3d: TMA SpMV work list: zc = %d, %zu items\n", zc, items.size());
         std::vector<WorkItem> &heavy = items;
