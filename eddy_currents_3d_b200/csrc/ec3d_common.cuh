@@ -58,6 +58,8 @@ struct SlabGeom {
     long long n_own;
     // global index (0-based, reference layout) of the first owned entry of each segment
     long long glob_off[4];
+    int vmap;                      // BLAS-1 kernels: 0 grid-stride, 1 one contiguous range per block
+    int vpad_;
 };
 
 // Local index of the U unknown of cell (i,j,k) (0-based global coordinates) in the dense U box.

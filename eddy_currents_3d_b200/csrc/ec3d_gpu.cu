@@ -884,6 +884,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     G.own_cum[0] = 0;
     for (int c = 0; c < 4; ++c) G.own_cum[c + 1] = G.own_cum[c] + G.own_len[c];
     G.n_own = G.own_cum[4];
+    { const char *ev = getenv("EC3D_VMAP"); G.vmap = ev ? atoi(ev) : 0; }
 
     // ---- coefficient tables ----
     build_coef(cfg->delta, cfg->dt, cfg->BND, h->cf);

@@ -374,24 +374,40 @@ k_cond_spmv(const SlabGeom G, const Coef cf, const MatCoef *__restrict__ mcs, co
 }
 
 // --------------------------------------------------------------------------------------------
-// K2': CSR SpMV on the reference's own arrays (drop-in mode), one thread per row, entries summed
-// sequentially in stored order like sprsAx (solvers.f90:54-61).
+// K2': CSR SpMV on the reference's own arrays (drop-in mode, sprsbcgstabwr_).  A block owns 256
+// consecutive rows; their (value, column) entries are one contiguous range of the CSR arrays, which
+// the block streams through shared memory with coalesced loads; each thread then sums ITS row
+// sequentially in stored order like sprsAx (solvers.f90:54-61), gathering x through L1/L2.
 // --------------------------------------------------------------------------------------------
+#define CSR_CH 4096
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_csr_spmv(const int n, const int *__restrict__ irow, const int *__restrict__ jcol, const double *__restrict__ valA,
            const VecSet vs, const IterCtl ctl, double *partials, const int pstride, const unsigned expected)
 {
     __shared__ double sh[64];
+    __shared__ double sprod[CSR_CH];
     if (!spmv_guard<MODE>(ctl)) return;
     double a0 = 0.0, a1 = 0.0;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) {
-        const int i1 = irow[r] - 1, i2 = irow[r + 1] - 1;
-        double s = 0.0;
-        for (int m = i1; m < i2; ++m) s = DADD(s, DMUL(__ldg(valA + m), vs.x[__ldg(jcol + m) - 1]));
-        row_epilogue<MODE>(s, r, vs.x[r], vs, a0, a1);
+    const int r0 = blockIdx.x * blockDim.x;
+    const int r = r0 + threadIdx.x;
+    const int rlast = min(r0 + (int)blockDim.x, n);
+    const long long lo = (long long)irow[r0] - 1, hi = (long long)irow[rlast] - 1;   // entries of this block's rows
+    long long i1 = 0, i2 = 0;
+    if (r < n) { i1 = (long long)irow[r] - 1; i2 = (long long)irow[r + 1] - 1; }
+    double s = 0.0;
+    for (long long c0 = lo; c0 < hi; c0 += CSR_CH) {
+        const int len = (int)min((long long)CSR_CH, hi - c0);
+        __syncthreads();
+        // products of the whole range: coalesced matrix stream, independent gathers of x
+        for (int q = threadIdx.x; q < len; q += blockDim.x)
+            sprod[q] = DMUL(__ldg(valA + c0 + q), vs.x[__ldg(jcol + c0 + q) - 1]);
+        __syncthreads();
+        // this thread's row: sequential sum in stored order (valA*x rounded, then added -- as sprsAx)
+        const long long ma = max(i1, c0), mb = min(i2, c0 + len);
+        for (long long m = ma; m < mb; ++m) s = DADD(s, sprod[m - c0]);
     }
+    if (r < n) row_epilogue<MODE>(s, r, vs.x[r], vs, a0, a1);
     if (MODE != MODE_PLAIN) {
         if (MODE == MODE_AP)
             reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), partials, pstride, blockIdx.x, expected, ctl.sc, RED_APR0, RED_APR0, sh);
@@ -411,6 +427,21 @@ __device__ __forceinline__ long long own_to_local(const SlabGeom &G, long long e
     return G.own_off[s] + (e - G.own_cum[s]);
 }
 
+// iteration space of a BLAS-1 kernel over `units` work units: grid-stride, or one contiguous range
+// per block (each SM then touches few 2 MB pages instead of all of them)
+struct QRange {
+    long long q0, q1, step;
+};
+__device__ __forceinline__ QRange q_range(const SlabGeom &G, const long long units)
+{
+    if (G.vmap) {
+        const long long per = (units + gridDim.x - 1) / gridDim.x;
+        const long long a = blockIdx.x * per;
+        return QRange{a + threadIdx.x, min(units, a + per), (long long)blockDim.x};
+    }
+    return QRange{blockIdx.x * (long long)blockDim.x + threadIdx.x, units, (long long)gridDim.x * blockDim.x};
+}
+
 // K3: alpha = rr0/(AP,R0); S = R - alpha*AP; ||S||^2.            solvers.f90:31-34
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -426,8 +457,8 @@ k_s_update(const SlabGeom G, const double *__restrict__ R, const double *__restr
     if (is_block0()) sc->alpha = alpha;
     dd acc = dd_zero();
     const long long units = G.n_own / VEC;
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < units;
-         q += (long long)gridDim.x * blockDim.x) {
+    const QRange qr = q_range(G, units);
+    for (long long q = qr.q0; q < qr.q1; q += qr.step) {
         const long long l = own_to_local(G, q * VEC);
         if (VEC == 2) {
             const double2 r = *reinterpret_cast<const double2 *>(R + l);
@@ -459,10 +490,10 @@ k_xr_update(const SlabGeom G, double *__restrict__ X, const double *__restrict__
     if (sc->done) return;
     const double alpha = sc->alpha;
     const long long units = G.n_own / VEC;
-    const long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long qs = (long long)gridDim.x * blockDim.x;
+    const QRange qr = q_range(G, units);
+    const long long q0 = qr.q0, qs = qr.step, qe = qr.q1;
     if (s_converged(sc)) {
-        for (long long q = q0; q < units; q += qs) {
+        for (long long q = q0; q < qe; q += qs) {
             const long long l = own_to_local(G, q * VEC);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) X[l + v] = DADD(X[l + v], DMUL(alpha, P[l + v]));
@@ -472,7 +503,7 @@ k_xr_update(const SlabGeom G, double *__restrict__ X, const double *__restrict__
     const double omega = sc->red[RED_ASS] / sc->red[RED_ASAS];
     if (is_block0()) sc->omega = omega;
     dd a0 = dd_zero(), a1 = dd_zero();
-    for (long long q = q0; q < units; q += qs) {
+    for (long long q = q0; q < qe; q += qs) {
         const long long l = own_to_local(G, q * VEC);
         if (VEC == 2) {
             double2 x = *reinterpret_cast<const double2 *>(X + l);
@@ -531,17 +562,29 @@ k_p_update(const SlabGeom G, double *__restrict__ P, const double *__restrict__ 
         if (restart) sc->restarts += 1;
     }
     const long long units = G.n_own / VEC;
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < units;
-         q += (long long)gridDim.x * blockDim.x) {
+    const QRange qr = q_range(G, units);
+    for (long long q = qr.q0; q < qr.q1; q += qr.step) {
         const long long l = own_to_local(G, q * VEC);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const double r = R[l + v];
+        if (VEC == 2) {
+            const double2 r = *reinterpret_cast<const double2 *>(R + l);
             if (restart) {
-                R0[l + v] = r;
-                P[l + v] = r;
+                *reinterpret_cast<double2 *>(R0 + l) = r;
+                *reinterpret_cast<double2 *>(P + l) = r;
             } else {
-                P[l + v] = DADD(r, DMUL(beta, DSUB(P[l + v], DMUL(omega, AP[l + v]))));
+                const double2 p = *reinterpret_cast<const double2 *>(P + l);
+                const double2 ap = *reinterpret_cast<const double2 *>(AP + l);
+                double2 o;
+                o.x = DADD(r.x, DMUL(beta, DSUB(p.x, DMUL(omega, ap.x))));
+                o.y = DADD(r.y, DMUL(beta, DSUB(p.y, DMUL(omega, ap.y))));
+                *reinterpret_cast<double2 *>(P + l) = o;
+            }
+        } else {
+            const double r = R[l];
+            if (restart) {
+                R0[l] = r;
+                P[l] = r;
+            } else {
+                P[l] = DADD(r, DMUL(beta, DSUB(P[l], DMUL(omega, AP[l]))));
             }
         }
     }

@@ -299,6 +299,9 @@ class Handle:
     def get_fields_raw(self, u_ptr: int, j_ptr: int):
         _check(load().ec3d_get_fields(self._h, u_ptr, j_ptr))
 
+    def set_fields_raw(self, u_ptr: int, j_ptr: int):
+        _check(load().ec3d_set_fields(self._h, u_ptr, j_ptr))
+
     def counters(self) -> dict:
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_double(), C.c_double()
         _check(load().ec3d_counters(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
