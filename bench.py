@@ -124,11 +124,17 @@ def oracle_ms_per_iter(grid: int, iters: int):
     return 1e3 * dt / max(it, 1), it, t_asm, p.nCells
 
 
-def recorded_iters(grid: int):
+def recorded_iters(grid: int, first: int = 0, count: int = 0):
+    """Mean BiCGSTABwr iterations per timestep of the GPU arm on plate(grid), steps [first, first+count)
+    when the record has them (the iteration counts are deterministic: same for every GPU count)."""
     try:
         with open(ITERS_FILE) as fh:
-            d = json.load(fh)
-        return float(d[str(grid)]["mean_iters_per_step"]), d[str(grid)].get("source", "")
+            d = json.load(fh)[str(grid)]
+        by_step = d.get("iters_by_step")
+        if by_step and count > 0 and first + count <= len(by_step):
+            sel = by_step[first:first + count]
+            return float(np.mean(sel)), f"recorded GPU-arm iteration counts of timesteps {first}..{first + count - 1}: {sel}"
+        return float(d["mean_iters_per_step"]), d.get("source", "")
     except Exception:
         return None, ""
 
@@ -151,7 +157,7 @@ def run_reference(args):
             per.append(ms_it)
     ms_iter_sample = float(np.mean(per))
     scale = (grid / sample_grid) ** 3            # CSR SpMV + vector passes are linear in the cell count
-    mean_it, src = recorded_iters(grid)
+    mean_it, src = recorded_iters(grid, args.warmup, args.steps)
     if mean_it is None:
         mean_it, src = 100.0, "assumed 100 iterations/step (no recorded GPU run)"
     ms_step = ms_iter_sample * scale * mean_it
@@ -178,9 +184,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=int(os.environ.get("EC3D_BENCH_GRID", "512")))
     ap.add_argument("--variant", default="A")
-    ap.add_argument("--ref-grid", type=int, default=128, help="grid of the bounded CPU sample (reference arm)")
-    ap.add_argument("--ref-iters", type=int, default=6)
-    ap.add_argument("--cpu-grid", type=int, default=96, help="grid of the in-line cpu_baseline sample")
+    ap.add_argument("--ref-grid", type=int, default=160, help="grid of the bounded CPU sample (reference arm)")
+    ap.add_argument("--ref-iters", type=int, default=15)
+    ap.add_argument("--cpu-grid", type=int, default=160, help="grid of the in-line cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--record-iters", action="store_true", help="write profiles/bench_iters.json")
     args = ap.parse_args()
@@ -231,8 +237,9 @@ def main():
         return h.step_raw(fsrc.data_ptr(), 0)
 
     step = 0
+    warm_iters = []
     for _ in range(args.warmup):
-        do_step(step); step += 1
+        warm_iters.append(do_step(step)); step += 1
     # Both timed regions run the SAME timesteps (same iteration counts): snapshot the fields after the
     # warm-up and restore them before the end-to-end region (plate variants A/B have no moving coil,
     # so Uaf/Jaf are the whole state).
@@ -340,9 +347,10 @@ def main():
             d = {}
             if os.path.exists(ITERS_FILE):
                 d = json.load(open(ITERS_FILE))
-            d[str(grid)] = {"mean_iters_per_step": float(np.mean(iters + iters2)),
-                            "iters": iters + iters2, "warmup": args.warmup,
-                            "source": "iteration counts of the GPU arm (equal to the oracle's in the parity tests)"}
+            d[str(grid)] = {"mean_iters_per_step": float(np.mean(warm_iters + iters)),
+                            "iters_by_step": warm_iters + iters, "warmup": args.warmup,
+                            "source": "iteration counts of the GPU arm by timestep (deterministic; identical for 1/2/4/8 GPUs; "
+                                      "equal to the oracle's where the oracle was run, see tests)"}
             os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
             out = os.path.join(ROOT, "gpurun_out", "bench_iters.json")
             os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -354,11 +362,11 @@ def main():
             from oracle import oracle
             oracle.build()
             cg = min(args.cpu_grid, grid)
-            ms_it, it, t_asm, _ = oracle_ms_per_iter(cg, 10)
+            ms_it, it, t_asm, _ = oracle_ms_per_iter(cg, 30)
             scale = (grid / cg) ** 3
             line["cpu_baseline"] = {
                 "value": ms_it * scale * mean_it, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"10 BiCGSTABwr iterations on plate({cg}) with the oracle's CSR, 1 thread; extrapolated "
+                "sample": f"30 BiCGSTABwr iterations on plate({cg}) with the oracle's CSR, 1 thread; extrapolated "
                           f"x{scale:.0f} cells and x{mean_it:.1f} iterations/step (this run's GPU count); "
                           f"oracle assembly {t_asm:.1f} s not included",
                 "ms_per_iteration_sample": ms_it}

@@ -110,13 +110,15 @@ extern "C" int ec3d_partition_planes(int32_t sdx, int32_t sdy, int32_t sdz, cons
                                      int32_t nranks, int32_t *kstart)
 {
     if (nranks < 1 || sdz < 2 * nranks || !kstart) { ec3d_set_error("partition: need sdz >= 2*nranks"); return EC3D_ERR_ARG; }
-    // bytes one BiCGSTABwr iteration moves per plane: 19 vector passes over 3 A unknowns per cell
-    // and 1 U unknown per conductor cell, plus the geoPHYS_C map read by the two SpMVs
+    // cost of one BiCGSTABwr iteration per plane, in bytes moved: 19 vector passes over 3 A unknowns per
+    // cell and 1 U unknown per conductor cell, the class map read by the two SpMVs -- plus, per conductor
+    // cell, the extra SpMV work of planes with conductor cells (their items run at about half the rate of
+    // conductor-free ones, measured on plate(256/512); SpMV is ~30 % of an iteration)
     const double kdz = (double)sdx * sdy;
     std::vector<double> w(sdz), cum(sdz + 1, 0.0);
     for (int k = 0; k < sdz; ++k) {
         const double nc = cond_per_plane ? (double)cond_per_plane[k] : 0.0;
-        w[k] = 152.0 * (3.0 * kdz + nc) + 2.0 * 4.0 * kdz + 120.0 * nc;
+        w[k] = 152.0 * (3.0 * kdz + nc) + 2.0 * 4.0 * kdz + 240.0 * nc;
         cum[k + 1] = cum[k] + w[k];
     }
     kstart[0] = 0;
@@ -419,7 +421,6 @@ struct ec3d_handle {
     MatCoef mc0{};
     bool tma = false;                    // k_spmv_tma usable (even sdx); else k_air_spmv + k_cond_spmv
     int nstage = 4;                      // depth of the TMA ring (EC3D_NSTAGE = 3, 4, 5)
-    int dbg = 0;                         // EC3D_DBG: timing experiments only
     CUtensorMap tmA[EC3D_NVEC], tmU[EC3D_NVEC];   // per local vector: A part (4-D), dense U box (3-D)
     CUtensorMap tmPA[EC3D_NVEC], tmPU[EC3D_NVEC]; // same tensors with halo-free 64 x 8 boxes (L2 prefetch of r0 / b)
     CUtensorMap tmC;                     // class bytes (3-D, uint8)
@@ -545,14 +546,6 @@ static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
         const double *auxp = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : vs.x;
         long long va = (auxp - h->vecs) / h->G.ltot;
         if (va < 0 || va >= EC3D_NVEC) va = v;            // (only used for an L2 prefetch)
-        if (h->dbg && MODE == MODE_AS) {               // timing experiments only (EC3D_DBG)
-#define DBGL(D) k_spmv_tma<MODE_AS, 4, D><<<h->airGrid, dim3(32, 8), tma::smem_bytes(4), h->st>>>( \
-            h->tmA[v], h->tmU[v], h->tmC, h->tmPA[va], h->tmPU[va], h->G, h->cf, h->mc0, h->d_items, vs, ctl, s.partials, \
-            s.pstride, (unsigned)h->nblkAir, 1)
-            switch (h->dbg) { case 1: DBGL(1); break; case 7: DBGL(7); break; case 8: DBGL(8); break; case 16: DBGL(16); break;
-                              default: DBGL(32); break; }
-#undef DBGL
-        } else
         switch (h->nstage) {
         case 3: launch_tma<MODE, 3>(h, (int)v, (int)va, vs, ctl); break;
         case 5: launch_tma<MODE, 5>(h, (int)v, (int)va, vs, ctl); break;
@@ -784,9 +777,6 @@ static cudaError_t set_attr_modes()
 }
 static int set_tma_smem_attr()
 {
-#define DBGA(D) CUDA_TRY(cudaFuncSetAttribute(k_spmv_tma<MODE_AS, 4, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::smem_bytes(4)))
-    DBGA(1); DBGA(7); DBGA(8); DBGA(16); DBGA(32);
-#undef DBGA
     CUDA_TRY(set_attr_modes<3>());
     CUDA_TRY(set_attr_modes<4>());
     CUDA_TRY(set_attr_modes<5>());
@@ -1002,8 +992,6 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         h->tma = (sdx % 2 == 0) && !(ef && atoi(ef) == 0);
         const char *en = getenv("EC3D_NSTAGE");
         h->nstage = (en && (atoi(en) == 3 || atoi(en) == 5)) ? atoi(en) : 4;
-        const char *ed = getenv("EC3D_DBG");
-        h->dbg = ed ? atoi(ed) : 0;
     }
     if (h->tma) {
         h->clsx = (sdx + 15) & ~15;

@@ -270,7 +270,7 @@ struct TmaCtx {             // per-thread constants of k_spmv_tma
 };
 
 // Plane loop of one work item.  HAS_U = item contains conductor cells.
-template <int MODE, int NSTAGE, bool HAS_U, int DBG>
+template <int MODE, int NSTAGE, bool HAS_U>
 __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUtensorMap &tmU, const CUtensorMap &tmC,
                                                const CUtensorMap &tmAuxA, const CUtensorMap &tmAuxU, const SlabGeom &G,
                                                const Coef &cf, const MatCoef &mc, const VecSet &vs, const TmaCtx &t,
@@ -379,19 +379,12 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
 #pragma unroll
                         for (int a = 0; a < 3; ++a) {
                             const double *tt = xs + a * TILE_D + o_own;
-                            const double2 ym = (DBG & 4) ? m[a] : *reinterpret_cast<const double2 *>(tt - BW);
-                            const double2 yp = (DBG & 4) ? z1[a] : *reinterpret_cast<const double2 *>(tt + BW);
-                            const double xm = (DBG & 4) ? c[a].y : tt[-1], xp = (DBG & 4) ? c[a].x : tt[2];
-                            double ya, yb;
-                            if (DBG & 2) {
-                                ya = DADD(DADD(DADD(m[a].x, ym.x), DADD(xm, c[a].x)), DADD(yp.x, z1[a].x));
-                                yb = DADD(DADD(DADD(m[a].y, ym.y), DADD(xp, c[a].y)), DADD(yp.y, z1[a].y));
-                            } else {
-                                ya = row7(czm, t.cym, cf.msx, dgA, t.cxpA, t.cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
-                                yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
-                            }
-                            if (DBG & 1) { a0 = DADD(a0, ya); a1 = DADD(a1, yb); }
-                            else pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
+                            const double2 ym = *reinterpret_cast<const double2 *>(tt - BW);
+                            const double2 yp = *reinterpret_cast<const double2 *>(tt + BW);
+                            const double xm = tt[-1], xp = tt[2];
+                            const double ya = row7(czm, t.cym, cf.msx, dgA, t.cxpA, t.cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
+                            const double yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
                         }
                     } else if (ca == 0x40 && cb == 0x40) {
                         // ---- both cells are interior conductor cells (all six neighbours conductor):
@@ -514,7 +507,7 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
     }
 }
 
-template <int MODE, int NSTAGE, int DBG = 0>
+template <int MODE, int NSTAGE>
 __global__ void __launch_bounds__(256, 2)
 k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmU,
            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAuxA,
@@ -556,9 +549,8 @@ k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     __syncthreads();
 
     dd a0 = dd_zero(), a1 = dd_zero();
-    if ((DBG & 16) && !w.has_u) return;                  // timing experiment: heavy items only
-    if (w.has_u && !(DBG & 8)) tma_plane_loop<MODE, NSTAGE, true, DBG>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
-    else if (!((DBG & 32) && w.has_u)) tma_plane_loop<MODE, NSTAGE, false, DBG>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
+    if (w.has_u) tma_plane_loop<MODE, NSTAGE, true>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
+    else         tma_plane_loop<MODE, NSTAGE, false>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
 
     if (MODE != MODE_PLAIN) {
         const int pidx = blockIdx.x;
