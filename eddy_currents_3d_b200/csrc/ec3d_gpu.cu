@@ -427,6 +427,7 @@ struct ec3d_handle {
     int clsx = 0;                        // row pitch of d_cls (sdx rounded up to 16)
     WorkItem *d_items = nullptr;         // (tile column, z range) work list of k_spmv_tma
     double *d_ucompact = nullptr;        // staging of the U block in the reference's compact numbering
+    float *d_out = nullptr;              // staging of one float32 output field (ec3d_get_vtk_fields)
     long long u_glob0 = 0;               // 0-based global index of this rank's first U unknown
     long long n_unknowns_own = 0;        // owned unknowns (without the padding of the dense U box)
     double valdom = 0.0;
@@ -598,7 +599,7 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     cudaFree(h->d_cb); cudaFree(h->d_cl); cudaFree(h->d_gather);
     if (h->comm) ncclCommDestroy(h->comm);
     cudaFree(h->d_mc); cudaFree(h->d_geo); cudaFree(h->d_mat); cudaFree(h->d_cond_cells); cudaFree(h->d_flags);
-    cudaFree(h->d_cls); cudaFree(h->d_ucompact); cudaFree(h->d_items);
+    cudaFree(h->d_cls); cudaFree(h->d_ucompact); cudaFree(h->d_items); cudaFree(h->d_out);
     cudaFree(h->vecs); cudaFree(h->sol.sc); cudaFree(h->sol.iter_base); cudaFree(h->sol.partials);
     cudaFree(h->d_nod_ptr); cudaFree(h->d_nods); cudaFree(h->d_num_Vmech); cudaFree(h->d_comp);
     cudaFree(h->d_new_nodes); cudaFree(h->d_ms); cudaFree(h->d_fun_vely); cudaFree(h->d_vmech); cudaFree(h->d_oob);
@@ -1234,6 +1235,34 @@ extern "C" int ec3d_set_fields(ec3d_handle *h, const double *Uaf, const double *
     if (Uaf && (rc = copy_in(h, h->Uaf, Uaf))) return rc;
     if (Jaf && (rc = copy_in(h, h->Jaf, Jaf))) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->st));
+    return EC3D_OK;
+}
+
+extern "C" int ec3d_get_vtk_fields(ec3d_handle *h, float *field_A, float *field_eddy, float *field_source, float *field_B,
+                                   int32_t big_endian)
+{
+    if (!h) return EC3D_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const SlabGeom &G = h->G;
+    const long long cells = (long long)G.nzl * G.kdz;
+    if (!h->d_out) CUDA_TRY(cudaMalloc(&h->d_out, (size_t)cells * 3 * sizeof(float)));
+    float *dst[4] = {field_A, field_eddy, field_source, field_B};
+    if (field_B && h->nranks > 1) {          // curl A reads Az, Ay, Ax of the planes k0-1 and k1
+        if (h->p2p) { k_reduce_xchg<<<1, 32, 0, h->st>>>(h->pt, h->sol.sc, 0, 0, 1, h->d_cl); LAUNCHED(h->launches); }
+        int rc = h_halo(h, h->Uaf);
+        if (rc) return rc;
+    }
+    const int nb = (int)std::max<long long>(1, std::min<long long>((cells + 255) / 256, 148 * 16));
+    for (int w = 0; w < 4; ++w) {
+        if (!dst[w]) continue;
+        k_vtk_field<<<nb, 256, 0, h->st>>>(G, h->d_geo, h->Uaf, h->Jaf, w, h->size_PHYS_C != 0 ? 1 : 0, h->delta[0], h->delta[1],
+                                           h->delta[2], big_endian, h->d_out);
+        LAUNCHED(h->launches);
+        CUDA_TRY(cudaMemcpyAsync(dst[w] + 3 * (long long)G.k0 * G.kdz, h->d_out, (size_t)cells * 3 * sizeof(float),
+                                 cudaMemcpyDeviceToHost, h->st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    CUDA_TRY(cudaGetLastError());
     return EC3D_OK;
 }
 

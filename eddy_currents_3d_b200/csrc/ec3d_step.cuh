@@ -165,3 +165,50 @@ k_rhs_post(const SlabGeom G, const int *__restrict__ cond_cells, const int ncond
         else Jaf[idx] = DSUB(DMUL(valdom, Uaf[idx]), Jaf[idx]);
     }
 }
+
+// Output post-processing on the device (writeVtk_field, utilites.f90:222-290): the
+// per-point float32 triples of a field_N.vtk in file order, for the owned planes.  what: 0 Field_A
+// (= Uaf), 1 Vector_field_eddy (s*Jaf on conductor cells, 0 elsewhere), 2 Vector_field_SOURCE (Jaf on
+// non-conductor cells; all cells without a conductor), 3 Vector_field_B (curl A, central differences,
+// indices clamped at the domain faces; needs fresh Uaf halo planes).  fp64 in the reference's order,
+// one rounding to float; big_endian != 0 byte-swaps like convert="big_endian" (:192).
+__device__ __forceinline__ float out_f(const double v, const int big_endian)
+{
+    const float f = __double2float_rn(v);
+    if (!big_endian) return f;
+    return __uint_as_float(__byte_perm(__float_as_uint(f), 0u, 0x0123));
+}
+
+__global__ void __launch_bounds__(256)
+k_vtk_field(const SlabGeom G, const int *__restrict__ geo, const double *__restrict__ Uaf, const double *__restrict__ Jaf,
+            const int what, const int has_conductor, const double d0, const double d1, const double d2,
+            const int big_endian, float *__restrict__ out)
+{
+    const long long cells = (long long)G.nzl * G.kdz;
+    const double sfac = -0.07957747154594766788444e7;             // utilites.f90:239
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < cells; q += (long long)gridDim.x * blockDim.x) {
+        const int kl = (int)(q / G.kdz), rem = (int)(q - (long long)kl * G.kdz), j = rem / G.sdx, i = rem - j * G.sdx;
+        const int k = G.k0 + kl;
+        const long long l = q + G.kdz;                            // local A offset (one halo plane below)
+        const int g = geo[q + 2 * (long long)G.kdz];              // geo planes start at k0-2
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (what == 0) {
+            v0 = Uaf[l]; v1 = Uaf[G.segA + l]; v2 = Uaf[2 * G.segA + l];
+        } else if (what == 1) {
+            if (has_conductor && g != 0) { v0 = DMUL(sfac, Jaf[l]); v1 = DMUL(sfac, Jaf[G.segA + l]); v2 = DMUL(sfac, Jaf[2 * G.segA + l]); }
+        } else if (what == 2) {
+            if (!has_conductor || g == 0) { v0 = Jaf[l]; v1 = Jaf[G.segA + l]; v2 = Jaf[2 * G.segA + l]; }
+        } else {
+            const long long im = (i == 0) ? l : l - 1, ip = (i == G.sdx - 1) ? l : l + 1;
+            const long long jm = (j == 0) ? l : l - G.sdx, jp = (j == G.sdy - 1) ? l : l + G.sdx;
+            const long long km = (k == 0) ? l : l - G.kdz, kp = (k == G.sdz - 1) ? l : l + G.kdz;
+            const double *A0 = Uaf, *A1 = Uaf + G.segA, *A2 = Uaf + 2 * G.segA;
+            v0 = DSUB(DMUL(0.5, DSUB(A2[jp], A2[jm])) / d1, DMUL(0.5, DSUB(A1[kp], A1[km])) / d2);
+            v1 = DSUB(DMUL(0.5, DSUB(A0[kp], A0[km])) / d2, DMUL(0.5, DSUB(A2[ip], A2[im])) / d0);
+            v2 = DSUB(DMUL(0.5, DSUB(A1[ip], A1[im])) / d0, DMUL(0.5, DSUB(A0[jp], A0[jm])) / d1);
+        }
+        out[3 * q] = out_f(v0, big_endian);
+        out[3 * q + 1] = out_f(v1, big_endian);
+        out[3 * q + 2] = out_f(v2, big_endian);
+    }
+}

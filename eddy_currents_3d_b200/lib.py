@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libec3d_gpu.so")
 EXPORTS = [
     "sprsbcgstabwr_", "ec3d_bicgstabwr_csr", "ec3d_csr_cache_clear", "ec3d_nccl_unique_id",
     "ec3d_create", "ec3d_destroy", "ec3d_sizes", "ec3d_assemble_csr", "ec3d_step", "ec3d_step_stage",
-    "ec3d_get_fields", "ec3d_set_fields", "ec3d_get_source_cells", "ec3d_apply_operator",
+    "ec3d_get_fields", "ec3d_set_fields", "ec3d_get_vtk_fields", "ec3d_get_source_cells", "ec3d_apply_operator",
     "ec3d_solve_host", "ec3d_bench_kernel", "ec3d_counters", "ec3d_timer_start", "ec3d_timer_stop", "ec3d_global_launch_count",
     "ec3d_last_error", "ec3d_version", "ec3d_partition_planes",
 ]
@@ -81,6 +81,8 @@ def load() -> C.CDLL:
     L.ec3d_get_fields.argtypes = [vp, vp, vp]
     L.ec3d_set_fields.restype = C.c_int
     L.ec3d_set_fields.argtypes = [vp, vp, vp]
+    L.ec3d_get_vtk_fields.restype = C.c_int
+    L.ec3d_get_vtk_fields.argtypes = [vp, vp, vp, vp, vp, i32]
     L.ec3d_get_source_cells.restype = C.c_int
     L.ec3d_get_source_cells.argtypes = [vp, vp]
     L.ec3d_apply_operator.restype = C.c_int
@@ -257,6 +259,13 @@ class Handle:
         U = None if U is None else np.ascontiguousarray(U, np.float64)
         J = None if J is None else np.ascontiguousarray(J, np.float64)
         _check(load().ec3d_set_fields(self._h, _p(U), _p(J)))
+
+    def vtk_fields(self, big_endian: bool = False):
+        """writeVtk_field's arrays (Field_A, Vector_field_eddy, Vector_field_SOURCE, Vector_field_B),
+        float32, shape (nCells, 3), computed on the device (utilites.f90:222-290)."""
+        out = [np.zeros((self.nCells, 3), np.float32) for _ in range(4)]
+        _check(load().ec3d_get_vtk_fields(self._h, *[_p(a) for a in out], 1 if big_endian else 0))
+        return tuple(out)
 
     def source_cells(self) -> np.ndarray:
         n = sum(len(s.nods) for s in self.problem.sources)

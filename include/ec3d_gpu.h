@@ -15,6 +15,8 @@
  *                                             motion_calc/new_m :1052-1114, inertial sources,
  *                                             solve, history update)
  *   ec3d_get_fields / ec3d_set_fields ....... the Uaf / Jaf arrays, EC3D.f90:55,148
+ *   ec3d_get_vtk_fields ..................... the field arithmetic of SUBROUTINE writeVtk_field,
+ *                                             utilites.f90:222-290 (output step, EC3D.f90:436-444)
  */
 #ifndef EC3D_GPU_H
 #define EC3D_GPU_H
@@ -131,6 +133,17 @@ int ec3d_step_stage(ec3d_handle *h, int32_t what, const double *fun_vely,
  * pointer may be NULL. */
 int ec3d_get_fields(ec3d_handle *h, double *Uaf, double *Jaf);
 int ec3d_set_fields(ec3d_handle *h, const double *Uaf, const double *Jaf);
+
+/* Output post-processing on the device (writeVtk_field, utilites.f90:222-290): the per-point float32
+ * triples of a field_N.vtk in file order (x fastest; 3 components per point; 3*nCells floats per
+ * array): field_A = Uaf; field_eddy = s*Jaf on conductor cells, 0 elsewhere (:237-250, meaningful
+ * when size_PHYS_C != 0); field_source = Jaf on non-conductor cells (:253-274); field_B = curl A by
+ * central differences with clamped indices (:276-290).  Computed in fp64 in the reference's order and
+ * rounded once.  big_endian != 0 stores the bytes as the reference's convert="big_endian" stream
+ * expects, so the host can write the arrays straight into the file.  Any pointer may be NULL.  With
+ * nranks > 1 each rank fills only the points of its z-slab. */
+int ec3d_get_vtk_fields(ec3d_handle *h, float *field_A, float *field_eddy, float *field_source,
+                        float *field_B, int32_t big_endian);
 
 /* Moved source cells of the last step in (function, node) order (new_nodesX/Y, EC3D.f90:311-320):
  * cell numbers 1..nC. */

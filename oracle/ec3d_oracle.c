@@ -742,3 +742,61 @@ void orc_rhs_post(const orc_grid *g, const orc_conductors *c, const orc_csr *A, 
     for (int32_t i = 0; i < A->num_bndY; ++i) Uaf[A->cel_bndY[i] - 1] = 0.0;
     for (int32_t i = 0; i < A->num_bndZ; ++i) Uaf[A->cel_bndZ[i] - 1] = 0.0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* output post-processing, utilites.f90:222-290                                                 */
+/* ------------------------------------------------------------------------------------------ */
+void orc_vtk_fields(int32_t sdx, int32_t sdy, int32_t sdz, const double delta[3], const double *Uaf,
+                    const double *Jaf, const int32_t *geoPHYS_C, int32_t size_PHYS_C, float *fieldA,
+                    float *eddy, float *source, float *fieldB)
+{
+    const int64_t kdz = (int64_t)sdx * sdy, nCells = kdz * sdz;
+    const double s = -0.07957747154594766788444e7;                /* utilites.f90:239 */
+    int64_t m = 0;                                                /* 1-based running cell number */
+    for (int k = 1; k <= sdz; ++k)
+        for (int j = 1; j <= sdy; ++j)
+            for (int i = 1; i <= sdx; ++i) {
+                m = m + 1;
+                const int64_t o = 3 * (m - 1);
+                const int n = geoPHYS_C[m - 1];
+                if (fieldA) {                                     /* :222-233 */
+                    fieldA[o] = (float)Uaf[m - 1];
+                    fieldA[o + 1] = (float)Uaf[nCells + m - 1];
+                    fieldA[o + 2] = (float)Uaf[2 * nCells + m - 1];
+                }
+                if (eddy) {                                       /* :237-250 */
+                    if (size_PHYS_C != 0 && n != 0) {
+                        eddy[o] = (float)(s * Jaf[m - 1]);
+                        eddy[o + 1] = (float)(s * Jaf[nCells + m - 1]);
+                        eddy[o + 2] = (float)(s * Jaf[2 * nCells + m - 1]);
+                    } else {
+                        eddy[o] = eddy[o + 1] = eddy[o + 2] = 0.0f;
+                    }
+                }
+                if (source) {                                     /* :253-274 */
+                    if (size_PHYS_C == 0 || n == 0) {
+                        source[o] = (float)Jaf[m - 1];
+                        source[o + 1] = (float)Jaf[nCells + m - 1];
+                        source[o + 2] = (float)Jaf[2 * nCells + m - 1];
+                    } else {
+                        source[o] = source[o + 1] = source[o + 2] = 0.0f;
+                    }
+                }
+                if (fieldB) {                                     /* :276-290 */
+                    int64_t nim = m - 1, njm = m - sdx, nkm = m - kdz, nip = m + 1, njp = m + sdx, nkp = m + kdz;
+                    if (i == 1) nim = m;
+                    if (i == sdx) nip = m;
+                    if (j == 1) njm = m;
+                    if (j == sdy) njp = m;
+                    if (k == 1) nkm = m;
+                    if (k == sdz) nkp = m;
+                    const double *A0 = Uaf - 1, *A1 = Uaf + nCells - 1, *A2 = Uaf + 2 * nCells - 1;   /* 1-based views */
+                    const double sxm = 0.5 * (A2[njp] - A2[njm]) / delta[1] - 0.5 * (A1[nkp] - A1[nkm]) / delta[2];
+                    const double sym = 0.5 * (A0[nkp] - A0[nkm]) / delta[2] - 0.5 * (A2[nip] - A2[nim]) / delta[0];
+                    const double szm = 0.5 * (A1[nip] - A1[nim]) / delta[0] - 0.5 * (A0[njp] - A0[njm]) / delta[1];
+                    fieldB[o] = (float)sxm;
+                    fieldB[o + 1] = (float)sym;
+                    fieldB[o + 2] = (float)szm;
+                }
+            }
+}

@@ -116,6 +116,16 @@ void orc_rhs_pre(const orc_grid *g, const orc_conductors *c, const orc_csr *A, c
 void orc_rhs_post(const orc_grid *g, const orc_conductors *c, const orc_csr *A, double *Uaf,
                   double *Jaf);
 
+/* utilites.f90:222-290 (writeVtk_field): the four per-point float32 vector fields of a field_N.vtk in
+ * file order (x fastest, 3 components per point): Field_A = Uaf; Vector_field_eddy = s*Jaf on
+ * conductor cells, 0 elsewhere (s = -0.0795774715459...d7, only written when size_PHYS_C != 0);
+ * Vector_field_SOURCE = Jaf on non-conductor cells (all cells when size_PHYS_C == 0);
+ * Vector_field_B = curl A by central differences with the indices clamped at the domain faces.
+ * Values are computed in fp64 in the reference's order and rounded once to float.  Pointers may be NULL. */
+void orc_vtk_fields(int32_t sdx, int32_t sdy, int32_t sdz, const double delta[3], const double *Uaf,
+                    const double *Jaf, const int32_t *geoPHYS_C, int32_t size_PHYS_C, float *fieldA,
+                    float *eddy, float *source, float *fieldB);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,24 @@ def bicgstabwr(valA, irow, jcol, b, x, tolerance: float, itmax: int) -> int:
     return it.value
 
 
+def vtk_fields(problem, Uaf: np.ndarray, Jaf: np.ndarray):
+    """utilites.f90:222-290: (Field_A, Vector_field_eddy, Vector_field_SOURCE, Vector_field_B) as
+    float32 arrays of shape (nCells, 3) in file order."""
+    p = problem
+    L = lib()
+    L.orc_vtk_fields.restype = None
+    L.orc_vtk_fields.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    nC = p.nCells
+    out = [np.zeros((nC, 3), np.float32) for _ in range(4)]
+    delta = np.ascontiguousarray(p.delta, np.float64)
+    U = np.ascontiguousarray(Uaf, np.float64)
+    J = np.ascontiguousarray(Jaf, np.float64)
+    g = np.ascontiguousarray(p.geoPHYS_C, np.int32)
+    L.orc_vtk_fields(p.sdx, p.sdy, p.sdz, _p(delta), _p(U), _p(J), _p(g), len(p.cond_numdom), *[_p(a) for a in out])
+    return tuple(out)
+
+
 class Assembled:
     """Result of gen_sparse_matrix (EC3D.f90:465-1049)."""
 

@@ -213,3 +213,29 @@ def test_invalid_geometry_is_reported(oracle_mod):
     p.geoPHYS_C, p.cond_nod = number_conductor(v.reshape(-1), [1], p.nCells)
     A = oracle_mod.Assembled(p)
     assert A.rc == 1 and A.err_col <= 0
+
+
+def test_vtk_fields_restatement():
+    """orc_vtk_fields (utilites.f90:222-290): curl of a linear potential is exact in the interior and
+    halved at the faces (clamped indices), eddy / source fields are masked by geoPHYS_C."""
+    from eddy_currents_3d_b200 import plate
+    from oracle import oracle
+    p = plate(16, "A")
+    nC, n = p.nCells, p.nCellsGlob
+    i = np.arange(nC) % p.sdx
+    j = (np.arange(nC) // p.sdx) % p.sdy
+    U = np.zeros(n)
+    U[nC:2 * nC] = 3.0 * i * p.delta[0]            # Ay = 3 x  ->  Bz = dAy/dx = 3
+    U[0:nC] = -2.0 * j * p.delta[1]                # Ax = -2 y ->  Bz -= dAx/dy = +2
+    J = np.arange(n, dtype=np.float64)
+    A, E, S, B = oracle.vtk_fields(p, U, J)
+    g = p.geoPHYS_C.reshape(-1)
+    inner = (i > 0) & (i < p.sdx - 1) & (j > 0) & (j < p.sdy - 1)
+    assert np.allclose(B[inner, 2], 5.0, rtol=1e-6) and np.allclose(B[:, :2], 0.0)
+    corner = (i == 0) & (j == 0)
+    assert np.allclose(B[corner, 2], 2.5, rtol=1e-6)               # one-sided halves at the faces
+    assert np.array_equal(A[:, 0], U[:nC].astype(np.float32))
+    assert np.all(E[g == 0] == 0) and np.all(S[g != 0] == 0)
+    s = -0.07957747154594766788444e7
+    assert np.array_equal(E[g != 0, 1], (s * J[nC:2 * nC][g != 0]).astype(np.float32))
+    assert np.array_equal(S[g == 0, 2], J[2 * nC:3 * nC][g == 0].astype(np.float32))
