@@ -184,23 +184,3 @@ __global__ void k_compact_list(const SlabGeom G, const unsigned char *__restrict
     else v = geo[(long long)cell0 - (long long)(G.k0 - 2) * G.kdz];
     list[pos[q]] = v;
 }
-
-// Class map of the fused SpMV (owned planes): 0 air / domain face, 1 interior conductor cell (all six
-// neighbours conductor), 2 conductor-surface cell (handled by the list kernel).
-__global__ void k_build_cls(const SlabGeom G, const int *__restrict__ cond_cells, const int ncond,
-                            const unsigned char *__restrict__ flags, unsigned char *__restrict__ cls,
-                            int *__restrict__ isslow)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ncond) return;
-    const int slow = (flags[t] & 63) != 0;
-    cls[(long long)cond_cells[t] - (long long)G.k0 * G.kdz] = slow ? 2 : 1;
-    isslow[t] = slow;
-}
-
-__global__ void k_compact_cells(const int *__restrict__ cond_cells, const int ncond, const int *__restrict__ keep,
-                                const long long *__restrict__ pos, int *__restrict__ out)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < ncond && keep[t]) out[pos[t]] = cond_cells[t];
-}

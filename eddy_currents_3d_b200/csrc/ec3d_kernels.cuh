@@ -1,5 +1,6 @@
-// ec3d_kernels.cuh -- sm_100a kernels of the EC3D hot path: matrix-free SpMV (air + conductor
-// parts), CSR SpMV (drop-in mode), fused BiCGSTABwr vector kernels, deterministic reductions.
+// ec3d_kernels.cuh -- sm_100a kernels of the EC3D hot path: generic matrix-free SpMV (odd grids; the
+// main TMA-staged SpMV is in ec3d_tma.cuh), CSR SpMV (drop-in mode), fused BiCGSTABwr vector kernels,
+// double-double reductions.
 //
 // Arithmetic: fp64 with explicit round-to-nearest mul/add (__dmul_rn/__dadd_rn are never
 // contracted into FMA), each row summed in ascending column order starting from 0 -- the order of
