@@ -246,7 +246,7 @@ def main():
     restorable = not any(getattr(s_, "moving", False) for s_ in p.sources) and args.variant != "M"
     if restorable:
         h.get_fields_raw(U_host.data_ptr(), J_host.data_ptr())
-        U_snap, J_snap = U_host.clone().pin_memory(), J_host.clone().pin_memory()
+        U_snap, J_snap = U_host.clone(), J_host.clone()      # pageable: used once, keeps pinned memory small
     first_timed = step
     # ---- timed region 1: resident (value) ----
     c0 = h.counters()
