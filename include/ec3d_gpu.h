@@ -34,7 +34,7 @@ enum {
                                  (EC3D.f90:717-720, 924-936) or conductor on a domain face */
     EC3D_ERR_NNZ_OVERFLOW = 4,/* nnz does not fit the reference's default INTEGER */
     EC3D_ERR_UNSUPPORTED = 5, /* e.g. more than one conductor domain, SRCZ (B5) */
-    EC3D_ERR_NCCL = 6
+    EC3D_ERR_NCCL = 6         /* NCCL error, or a peer-to-peer exchange timed out waiting for a neighbour rank */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -92,8 +92,10 @@ typedef struct {
     const int32_t *fun_move;     /* [numfun][3] */
     const double *fun_vel_Vmech; /* [numfun][3] */
     int32_t numMech;
-    /* multi-GPU z-slab decomposition: this process is `rank` of `nranks`; nccl_id = 128 bytes
-     * from ec3d_nccl_unique_id() of rank 0 (ignored when nranks == 1) */
+    /* multi-GPU z-slab decomposition: this process is `rank` of `nranks` (one process per GPU);
+     * nccl_id = 128 bytes from ec3d_nccl_unique_id() of rank 0 (ignored when nranks == 1).  NCCL is
+     * used for set-up; halo planes and solver scalars then travel through NVLink peer memory (CUDA
+     * IPC), with NCCL send/recv/all-gather as the fallback.  Results are bit-identical for any nranks. */
     int32_t nranks, rank;
     const void *nccl_id;
     int32_t device;              /* CUDA device ordinal, -1 = current */
