@@ -420,7 +420,7 @@ struct ec3d_handle {
     int mat0 = 0;
     MatCoef mc0{};
     bool tma = false;                    // k_spmv_tma usable (even sdx); else k_air_spmv + k_cond_spmv
-    int nstage = 4;                      // depth of the TMA ring (EC3D_NSTAGE = 3, 4, 5)
+    int nstage = 0;                      // depth of the TMA ring forced by EC3D_NSTAGE = 3, 4, 5 (0: per mode)
     CUtensorMap tmA[EC3D_NVEC], tmU[EC3D_NVEC];   // per local vector: A part (4-D), dense U box (3-D)
     CUtensorMap tmPA[EC3D_NVEC], tmPU[EC3D_NVEC]; // same tensors with halo-free 64 x 8 boxes (L2 prefetch of r0 / b)
     CUtensorMap tmC;                     // class bytes (3-D, uint8)
@@ -547,7 +547,10 @@ static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
         const double *auxp = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : vs.x;
         long long va = (auxp - h->vecs) / h->G.ltot;
         if (va < 0 || va >= EC3D_NVEC) va = v;            // (only used for an L2 prefetch)
-        switch (h->nstage) {
+        // ring depth: the modes that also stream r0 / b through L1 (AP, INIT) measure faster with 3 stages
+        // (more of the 228 KB left as L1), the pure-TMA modes with 4; EC3D_NSTAGE overrides both
+        const int ns = h->nstage ? h->nstage : ((MODE == MODE_AP || MODE == MODE_INIT) ? 3 : 4);
+        switch (ns) {
         case 3: launch_tma<MODE, 3>(h, (int)v, (int)va, vs, ctl); break;
         case 5: launch_tma<MODE, 5>(h, (int)v, (int)va, vs, ctl); break;
         default: launch_tma<MODE, 4>(h, (int)v, (int)va, vs, ctl); break;
@@ -992,7 +995,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         const char *ef = getenv("EC3D_TMA");
         h->tma = (sdx % 2 == 0) && !(ef && atoi(ef) == 0);
         const char *en = getenv("EC3D_NSTAGE");
-        h->nstage = (en && (atoi(en) == 3 || atoi(en) == 5)) ? atoi(en) : 4;
+        h->nstage = (en && (atoi(en) == 3 || atoi(en) == 4 || atoi(en) == 5)) ? atoi(en) : 0;
     }
     if (h->tma) {
         h->clsx = (sdx + 15) & ~15;
