@@ -616,6 +616,91 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
 }
 
 // ------------------------------------------------------------------------------------------
+// work list of the TMA SpMV (host only; exported as ec3d_plan_spmv_items for the CPU tests)
+// ------------------------------------------------------------------------------------------
+// (tile column, z range) items.  Tile columns that touch the conductor's bounding box are split at
+// the box's first / last plane so that items are either free of conductor cells (lean 7-point loop)
+// or carry them (U tiles, class bytes, conductor rows; about twice the cost per plane, hence half
+// the length).  An item loads 2 planes more than it computes.
+static void plan_spmv_items(const SlabGeom &G, int zc, bool plane_major, std::vector<WorkItem> &items)
+{
+    const int tx = (G.sdx + tma::TX - 1) / tma::TX, ty = (G.sdy + tma::TY - 1) / tma::TY;
+    const int ck0 = std::max(G.k0, G.ub_k0), ck1 = std::min(G.k1, G.ub_k0 + G.ub_nz);   // conductor planes of this slab
+    // cuts on a GLOBAL z grid (multiples of zc; zc/2 inside the conductor's z range) so that the
+    // items of neighbouring tile columns cover the same planes and march in lock step
+    std::vector<WorkItem> light;
+    items.clear();
+    zc = std::max(zc, 2);
+    const int zh = std::max(2, zc / 2);
+    std::vector<int> cuts;
+    for (int by = 0; by < ty; ++by)
+        for (int bx = 0; bx < tx; ++bx) {
+            const int x0 = bx * tma::TX, y0 = by * tma::TY;
+            const bool touch = G.ub_nz > 0 && ck1 > ck0 && x0 < G.ub_i0 + G.ub_nx && x0 + tma::TX > G.ub_i0 &&
+                               y0 < G.ub_j0 + G.ub_ny && y0 + tma::TY > G.ub_j0;
+            cuts.clear();
+            cuts.push_back(G.k0); cuts.push_back(G.k1);
+            for (int k = (G.k0 / zc + 1) * zc; k < G.k1; k += zc) cuts.push_back(k);
+            if (touch) {
+                cuts.push_back(ck0); cuts.push_back(ck1);
+                for (int k = (ck0 / zh + 1) * zh; k < ck1; k += zh) cuts.push_back(k);
+            }
+            std::sort(cuts.begin(), cuts.end());
+            cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+            // segments; short ones are merged into the previous segment of the same kind
+            std::vector<WorkItem> col;
+            for (size_t q = 0; q + 1 < cuts.size(); ++q) {
+                const int ka = cuts[q], kb_ = cuts[q + 1];
+                const int has_u = (touch && ka >= ck0 && kb_ <= ck1) ? 1 : 0;
+                const int minlen = std::max(2, (has_u ? zh : zc) / 4);
+                if (!col.empty() && col.back().has_u == has_u && (kb_ - ka < minlen || col.back().ke - col.back().kb < minlen))
+                    col.back().ke = kb_;
+                else
+                    col.push_back(WorkItem{x0, y0, ka, kb_, has_u, 0, 0, 0});
+            }
+            for (const WorkItem &w : col) (w.has_u ? items : light).push_back(w);
+        }
+    items.insert(items.end(), light.begin(), light.end());   // items with conductor cells first ...
+    // ... then plane-major: CTAs that run at the same time work on neighbouring tiles of the same
+    // z range at the same z phase, so the y-halo rows a tile shares with its neighbours (2 of 10
+    // rows per box) are still in L2 when the neighbour asks for them (at 512^3 a column-major
+    // order re-reads them from HBM: +27 % DRAM reads)
+    if (plane_major)
+        std::stable_sort(items.begin(), items.end(), [](const WorkItem &a, const WorkItem &b) { return a.kb < b.kb; });
+}
+
+// Planes per item: measured on plate(256) / plate(512), 32..48 is the flat optimum (longer items
+// leave too few CTAs for the last round, shorter ones pay the 2 extra planes and the pipeline fill
+// more often); small grids get shorter items so that every SM has work.
+static int default_item_planes(const SlabGeom &G)
+{
+    const int tx = (G.sdx + tma::TX - 1) / tma::TX, ty = (G.sdy + tma::TY - 1) / tma::TY;
+    return (int)std::min<long long>(48, std::max<long long>(4, (long long)G.nzl * tx * ty / (2 * 148)));
+}
+
+extern "C" int ec3d_plan_spmv_items(int32_t sdx, int32_t sdy, int32_t k0, int32_t k1, const int32_t box[6], int32_t zc,
+                                    int32_t plane_major, int32_t *items5, int32_t max_items, int32_t *n_items)
+{
+    if (!box || !n_items || sdx < 1 || sdy < 1 || k1 <= k0) { ec3d_set_error("bad argument"); return EC3D_ERR_ARG; }
+    SlabGeom G;
+    memset(&G, 0, sizeof(G));
+    G.sdx = sdx; G.sdy = sdy; G.kdz = sdx * sdy; G.k0 = k0; G.k1 = k1; G.nzl = k1 - k0;
+    G.ub_i0 = box[0]; G.ub_nx = box[1] - box[0]; G.ub_j0 = box[2]; G.ub_ny = box[3] - box[2];
+    G.ub_k0 = box[4]; G.ub_nz = std::max(0, box[5] - box[4]);
+    std::vector<WorkItem> items;
+    plan_spmv_items(G, zc > 0 ? zc : default_item_planes(G), plane_major != 0, items);
+    *n_items = (int32_t)items.size();
+    if (items5) {
+        if ((int)items.size() > max_items) { ec3d_set_error("item buffer too small"); return EC3D_ERR_ARG; }
+        for (size_t q = 0; q < items.size(); ++q) {
+            items5[5 * q] = items[q].x0; items5[5 * q + 1] = items[q].y0; items5[5 * q + 2] = items[q].kb;
+            items5[5 * q + 3] = items[q].ke; items5[5 * q + 4] = items[q].has_u;
+        }
+    }
+    return EC3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // peer-to-peer exchange set-up: CUDA IPC mappings of the neighbours' vector allocations and of
 // every rank's CommBlock, agreed on by all ranks (any failure -> everybody stays on NCCL)
 // ------------------------------------------------------------------------------------------
@@ -1010,66 +1095,15 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         if (rc) return rc;
         rc = set_tma_smem_attr();
         if (rc) return rc;
-        // work list: (tile column, z range) items.  Tile columns that touch the conductor's bounding
-        // box are split at the box's first / last plane so that items are either free of conductor
-        // cells (lean 7-point loop) or carry them (U tiles, class bytes, conductor rows; about twice the
-        // cost per plane, hence half the length).  An item loads 2 planes more than it computes.
-        const int tx = (sdx + tma::TX - 1) / tma::TX, ty = (sdy + tma::TY - 1) / tma::TY;
-        const int ck0 = std::max(G.k0, G.ub_k0), ck1 = std::min(G.k1, G.ub_k0 + G.ub_nz);   // conductor planes of this slab
         const char *eo = getenv("EC3D_ORDER");
         const bool plane_major = !(eo && atoi(eo) == 0);
-        auto build_items = [&](int zc, std::vector<WorkItem> &items) {
-            // cuts on a GLOBAL z grid (multiples of zc; zc/2 inside the conductor's z range) so that the
-            // items of neighbouring tile columns cover the same planes and march in lock step
-            std::vector<WorkItem> light;
-            items.clear();
-            const int zh = std::max(2, zc / 2);
-            std::vector<int> cuts;
-            for (int by = 0; by < ty; ++by)
-                for (int bx = 0; bx < tx; ++bx) {
-                    const int x0 = bx * tma::TX, y0 = by * tma::TY;
-                    const bool touch = G.ub_nz > 0 && ck1 > ck0 && x0 < G.ub_i0 + G.ub_nx && x0 + tma::TX > G.ub_i0 &&
-                                       y0 < G.ub_j0 + G.ub_ny && y0 + tma::TY > G.ub_j0;
-                    cuts.clear();
-                    cuts.push_back(G.k0); cuts.push_back(G.k1);
-                    for (int k = (G.k0 / zc + 1) * zc; k < G.k1; k += zc) cuts.push_back(k);
-                    if (touch) {
-                        cuts.push_back(ck0); cuts.push_back(ck1);
-                        for (int k = (ck0 / zh + 1) * zh; k < ck1; k += zh) cuts.push_back(k);
-                    }
-                    std::sort(cuts.begin(), cuts.end());
-                    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
-                    // segments; short ones are merged into the previous segment of the same kind
-                    std::vector<WorkItem> col;
-                    for (size_t q = 0; q + 1 < cuts.size(); ++q) {
-                        const int ka = cuts[q], kb_ = cuts[q + 1];
-                        const int has_u = (touch && ka >= ck0 && kb_ <= ck1) ? 1 : 0;
-                        const int minlen = std::max(2, (has_u ? zh : zc) / 4);
-                        if (!col.empty() && col.back().has_u == has_u && (kb_ - ka < minlen || col.back().ke - col.back().kb < minlen))
-                            col.back().ke = kb_;
-                        else
-                            col.push_back(WorkItem{x0, y0, ka, kb_, has_u, 0, 0, 0});
-                    }
-                    for (const WorkItem &w : col) (w.has_u ? items : light).push_back(w);
-                }
-            items.insert(items.end(), light.begin(), light.end());   // items with conductor cells first ...
-            // ... then plane-major: CTAs that run at the same time work on neighbouring tiles of the same
-            // z range at the same z phase, so the y-halo rows a tile shares with its neighbours (2 of 10
-            // rows per box) are still in L2 when the neighbour asks for them (at 512^3 a column-major
-            // order re-reads them from HBM: +27 % DRAM reads)
-            if (plane_major)
-                std::stable_sort(items.begin(), items.end(), [](const WorkItem &a, const WorkItem &b) { return a.kb < b.kb; });
-        };
-        // zc: measured on plate(256) / plate(512), 32..48 planes per item is the flat optimum (longer items
-        // leave too few CTAs for the last round, shorter ones pay the 2 extra planes and the pipeline fill
-        // more often); small grids get shorter items so that every SM has work
         std::vector<WorkItem> items;
-        int zc = (int)std::min<long long>(48, std::max<long long>(4, (long long)G.nzl * tx * ty / (2 * 148)));
+        int zc = default_item_planes(G);
         {
             const char *ez = getenv("EC3D_ZC");
             if (ez && atoi(ez) > 0) zc = atoi(ez);
         }
-        build_items(zc, items);
+        plan_spmv_items(G, zc, plane_major, items);
         h->zc = zc;
         if (getenv("EC3D_VERBOSE")) fprintf(stderr, "ec3d: TMA SpMV work list: zc = %d, %zu items\n", zc, items.size());
         std::vector<WorkItem> &heavy = items;

@@ -20,7 +20,7 @@ EXPORTS = [
     "ec3d_create", "ec3d_destroy", "ec3d_sizes", "ec3d_assemble_csr", "ec3d_step", "ec3d_step_stage",
     "ec3d_get_fields", "ec3d_set_fields", "ec3d_get_vtk_fields", "ec3d_get_source_cells", "ec3d_apply_operator",
     "ec3d_solve_host", "ec3d_bench_kernel", "ec3d_counters", "ec3d_timer_start", "ec3d_timer_stop", "ec3d_global_launch_count",
-    "ec3d_last_error", "ec3d_version", "ec3d_partition_planes",
+    "ec3d_last_error", "ec3d_version", "ec3d_partition_planes", "ec3d_plan_spmv_items",
 ]
 
 
@@ -121,6 +121,19 @@ def partition_planes(sdx: int, sdy: int, sdz: int, cond_per_plane: np.ndarray, n
     ks = np.zeros(nranks + 1, np.int32)
     _check(load().ec3d_partition_planes(sdx, sdy, sdz, _p(cpp), nranks, _p(ks)))
     return ks
+
+
+def plan_spmv_items(sdx: int, sdy: int, k0: int, k1: int, box, zc: int = 0, plane_major: bool = True) -> np.ndarray:
+    """Host-only: work list of the TMA SpMV, rows {x0, y0, kb, ke, has_u} in launch order."""
+    L = load()
+    L.ec3d_plan_spmv_items.restype = C.c_int
+    L.ec3d_plan_spmv_items.argtypes = [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    b = np.ascontiguousarray(box, np.int32)
+    n = C.c_int32(0)
+    _check(L.ec3d_plan_spmv_items(sdx, sdy, k0, k1, _p(b), zc, 1 if plane_major else 0, None, 0, C.byref(n)))
+    out = np.zeros((max(n.value, 1), 5), np.int32)
+    _check(L.ec3d_plan_spmv_items(sdx, sdy, k0, k1, _p(b), zc, 1 if plane_major else 0, _p(out), n.value, C.byref(n)))
+    return out[:n.value]
 
 
 def nccl_unique_id() -> bytes:

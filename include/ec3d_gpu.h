@@ -192,6 +192,13 @@ const char *ec3d_version(void);
 int ec3d_partition_planes(int32_t sdx, int32_t sdy, int32_t sdz, const int64_t *cond_per_plane,
                           int32_t nranks, int32_t *kstart);
 
+/* Work list of the TMA-staged SpMV for a slab of planes [k0,k1) of an sdx x sdy x . grid whose conductor
+ * bounding box is box = {i0,i1,j0,j1,k0,k1} (half open, 0-based; k0 == k1: no conductor): items5 receives
+ * {x0, y0, kb, ke, has_u} per item in launch order (pass NULL to get only the count).  zc <= 0 selects the
+ * default item length.  Every (64 x 8 tile, plane) is covered by exactly one item. */
+int ec3d_plan_spmv_items(int32_t sdx, int32_t sdy, int32_t k0, int32_t k1, const int32_t box[6], int32_t zc,
+                         int32_t plane_major, int32_t *items5, int32_t max_items, int32_t *n_items);
+
 #ifdef __cplusplus
 }
 #endif

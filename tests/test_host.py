@@ -128,3 +128,38 @@ def test_partition_planes():
     assert counts[1:3].max() <= counts[4:].min()           # heavier planes -> fewer planes per rank
     with pytest.raises(lib.Ec3dError):
         lib.partition_planes(64, 64, 6, np.zeros(6, np.int64), 8)
+
+
+@pytest.mark.parametrize("case", [
+    # sdx, sdy, k0, k1, conductor box (i0,i1,j0,j1,k0,k1), zc
+    (256, 256, 0, 256, (32, 224, 32, 224, 32, 96), 0),       # plate(256), one GPU
+    (512, 512, 64, 128, (64, 448, 64, 448, 64, 192), 0),     # a slab of plate(512) inside the conductor range
+    (102, 102, 0, 24, (6, 96, 6, 96, 2, 8), 0),              # compare_to_Elmer.vxc: partial tiles in x and y
+    (176, 32, 5, 22, (2, 174, 2, 30, 9, 13), 3),             # LIM.vxc, upper slab, odd item length
+    (64, 40, 0, 16, (0, 0, 0, 0, 0, 0), 0),                  # no conductor
+])
+def test_spmv_work_list_covers_every_tile_plane_once(case):
+    """Host logic of the TMA SpMV (ec3d_plan_spmv_items): the (tile column, z range) items cover every
+    64 x 8 tile of every owned plane exactly once, items flagged has_u are exactly those that lie in
+    the conductor's z range and touch its footprint, unflagged items contain no conductor plane of a
+    touching column, and the launch order is plane-major."""
+    from eddy_currents_3d_b200 import lib
+    sdx, sdy, k0, k1, box, zc = case
+    it = lib.plan_spmv_items(sdx, sdy, k0, k1, box, zc)
+    tx, ty = (sdx + 63) // 64, (sdy + 7) // 8
+    cover = np.zeros((ty, tx, k1 - k0), np.int32)
+    i0, i1, j0, j1, b0, b1 = box
+    c0, c1 = max(k0, b0), min(k1, b1)
+    for x0, y0, ka, kb, has_u in it:
+        assert x0 % 64 == 0 and y0 % 8 == 0 and k0 <= ka < kb <= k1
+        cover[y0 // 8, x0 // 64, ka - k0:kb - k0] += 1
+        touch = b1 > b0 and c1 > c0 and x0 < i1 and x0 + 64 > i0 and y0 < j1 and y0 + 8 > j0
+        if has_u:
+            assert touch and c0 <= ka and kb <= c1
+        elif touch:
+            assert kb <= c0 or ka >= c1                       # lean items hold no conductor plane
+    assert np.all(cover == 1)
+    assert np.all(np.diff(it[:, 2]) >= 0)                       # plane-major launch order
+    # column-major order keeps the same set of items
+    it2 = lib.plan_spmv_items(sdx, sdy, k0, k1, box, zc, plane_major=False)
+    assert sorted(map(tuple, it)) == sorted(map(tuple, it2))
