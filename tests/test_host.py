@@ -163,3 +163,84 @@ def test_spmv_work_list_covers_every_tile_plane_once(case):
     # column-major order keeps the same set of items
     it2 = lib.plan_spmv_items(sdx, sdy, k0, k1, box, zc, plane_major=False)
     assert sorted(map(tuple, it)) == sorted(map(tuple, it2))
+
+
+def _synthetic_deck(tmp_path, compression: str):
+    """A small VoxCad deck written from scratch (no reference file needed): 16 x 12 x 10 grid, conductor
+    block (material 1), one x-directed and one y-directed coil bar (materials 2, 3), palette strings in
+    the reference's keyword syntax (vxc2data.f90:127-222, 443-548)."""
+    import base64
+    import zlib
+    sdx, sdy, sdz = 16, 12, 10
+    v = np.zeros((sdz, sdy, sdx), np.uint8)
+    v[2:6, 2:10, 3:13] = 1                       # conductor: k 2..5, j 2..9, i 3..12 (>= 3 thick, off the faces)
+    v[7, 3:5, 4:12] = 2                          # coil bar, SRCx
+    v[7, 5:9, 4:6] = 3                           # coil bar, SRCy
+    names = ["plast D=1 C='mu0*35.26e6'", "axp D=1 SRCx=Fp", "ayp D=1 SRCy=Fm", "param  tran stop=10m step=1m",
+             "p2 solver tol=5m itmax=500  dir=vec", "f1 func Fp=a*cos(p2*f*t) a='183/(2*dx*1*dz)' p2='2*pi' f=50 t=t ",
+             "f2 func Fm=a*cos(p2*f*t) a='-183/(2*dx*1*dz)' p2='2*pi' f=50 t=t "]
+    letters = "0123456789:;<=>?@ABCDEFGHIJKLMNOPQRSTUVWXYZ[\\]^_`abcdefghijklmnopqrstuvwxyz"
+    out = ["<?xml version=\"1.0\" encoding=\"ISO-8859-1\"?>", "<VXC Version=\"0.94\">", "<Lattice>",
+           "    <Lattice_Dim>0.004</Lattice_Dim>", "    <X_Dim_Adj>1</X_Dim_Adj>", "    <Y_Dim_Adj>1.25</Y_Dim_Adj>",
+           "    <Z_Dim_Adj>1</Z_Dim_Adj>", "</Lattice>", "<Palette>"]
+    for m, nm in enumerate(names, 1):
+        out += [f"    <Material ID=\"{m}\">", f"      <Name>{nm}</Name>", "    </Material>"]
+    out += ["</Palette>", f"  <Structure Compression=\"{compression}\">", f"    <X_Voxels>{sdx}</X_Voxels>",
+            f"    <Y_Voxels>{sdy}</Y_Voxels>", f"    <Z_Voxels>{sdz}</Z_Voxels>", "    <Data>"]
+    for k in range(sdz):
+        raw = v[k].reshape(-1)
+        if compression == "ZLIB":
+            payload = base64.b64encode(zlib.compress(raw.tobytes())).decode()
+        else:
+            payload = "".join(letters[int(b)] for b in raw)
+        out.append(f"      <Layer><![CDATA[{payload}]]></Layer>")
+    out += ["    </Data>", "  </Structure>", "</VXC>"]
+    path = tmp_path / f"deck_{compression}.vxc"
+    path.write_text("\n".join(out) + "\n")
+    return str(path), v
+
+
+def test_vxc_loader_synthetic_deck_zlib_and_ascii(tmp_path):
+    """Harness row N1: both voxel encodings of the reference (ZLIB+base64 layers, vxc2data.f90:253-296 and
+    uncompress_zlib.py; ASCII_READABLE letters '1'..'z', :298-311) give the same Problem, with the
+    numbering rules of vxc2data (geoPHYS_C = 3*nCells + m in k,j,i order, :609-652)."""
+    from eddy_currents_3d_b200 import load_vxc
+    pz, v = _synthetic_deck(tmp_path, "ZLIB")
+    pa, _ = _synthetic_deck(tmp_path, "ASCII_READABLE")
+    A, B = load_vxc(pz), load_vxc(pa)
+    assert (A.sdx, A.sdy, A.sdz) == (16, 12, 10)
+    assert np.allclose(A.delta, [0.004, 0.005, 0.004])
+    assert A.tolerance == 5e-3 and A.itmax == 500 and abs(A.dt - 1e-3) < 1e-18
+    for name in ("geoPHYS", "geoPHYS_C", "valPHYS", "delta", "BND"):
+        assert np.array_equal(getattr(A, name), getattr(B, name)), name
+    assert len(A.sources) == len(B.sources) == 2
+    for sa, sb in zip(A.sources, B.sources):
+        assert np.array_equal(sa.nods, sb.nods)
+    # conductor numbering: consecutive in k,j,i order, starting at 3*nCells + 1
+    g = A.geoPHYS_C.reshape(-1)
+    cond = np.flatnonzero(v.reshape(-1) == 1)
+    assert np.array_equal(np.flatnonzero(g), cond)
+    assert np.array_equal(g[cond], 3 * A.nCells + 1 + np.arange(cond.size))
+    assert A.nCellsGlob == 3 * A.nCells + cond.size
+    # coil cells: SRCx nodes are plain cell numbers, SRCy nodes are offset by nCells (EC3D.f90:203-230)
+    assert set(A.sources[0].nods) == set(np.flatnonzero(v.reshape(-1) == 2) + 1)
+    assert set(A.sources[1].nods) == set(np.flatnonzero(v.reshape(-1) == 3) + 1 + A.nCells)
+    f0, _ = A.source_scalars(0.0)
+    assert f0[0] > 0 > f0[1] and abs(f0[0] + f0[1]) < 1e-12 * abs(f0[0])
+
+
+def test_synthetic_deck_runs_through_the_oracle(tmp_path):
+    """A user deck that is not one of the three shipped ones goes from .vxc text to converged timesteps
+    on the CPU oracle (loader + expression evaluator + assembly + BiCGSTABwr)."""
+    from eddy_currents_3d_b200 import load_vxc
+    from oracle import oracle
+    path, _ = _synthetic_deck(tmp_path, "ASCII_READABLE")
+    p = load_vxc(path)
+    run = oracle.OracleRun(p)
+    assert run.A.rc == 0 and run.A.num_nz == run.A.irow[-1] - 1
+    its = []
+    for _ in range(2):
+        f, v = p.source_scalars(run.T)
+        its.append(run.step(f, v))
+    assert all(0 < it <= p.itmax for it in its), its          # converged (the reference runs itmax+1 otherwise)
+    assert np.isfinite(run.Uaf).all() and np.isfinite(run.Jaf).all() and np.abs(run.Uaf).max() > 0
