@@ -225,7 +225,7 @@ def main():
     h = lib.Handle(p, nranks=world, rank=rank, nccl_id=nccl_id, device=local)
     t_create = time.perf_counter() - t0
     n, nC = p.nCellsGlob, p.nCells
-    nsteps_total = args.warmup + 2 * args.steps
+    nsteps_total = args.warmup + args.steps
     scal = [p.source_scalars(s * p.dt) for s in range(nsteps_total)]
     # pinned host buffers: per-step scalars in, full fields out
     fsrc = torch.zeros(max(p.numfun, 1), dtype=torch.float64).pin_memory()
@@ -240,41 +240,29 @@ def main():
     warm_iters = []
     for _ in range(args.warmup):
         warm_iters.append(do_step(step)); step += 1
-    # Both timed regions run the SAME timesteps (same iteration counts): snapshot the fields after the
-    # warm-up and restore them before the end-to-end region (plate variants A/B have no moving coil,
-    # so Uaf/Jaf are the whole state).
-    restorable = not any(getattr(s_, "moving", False) for s_ in p.sources) and args.variant != "M"
-    if restorable:
         h.get_fields_raw(U_host.data_ptr(), J_host.data_ptr())
-        U_snap, J_snap = U_host.clone(), J_host.clone()      # pageable: used once, keeps pinned memory small
-    first_timed = step
-    # ---- timed region 1: resident (value) ----
+    # ---- ONE timed region, two clocks over the same K steps ----
+    #   value : device time of the hot path (CUDA events recorded by ec3d_step on the library's stream
+    #           around scatter + RHS + solve + history update), fields resident in HBM
+    #   e2e   : wall clock around [step through the C ABI with pinned host scalars] + [D2H of the full
+    #           Uaf / Jaf into pinned host memory], i.e. what the Fortran host sees per timestep
     c0 = h.counters()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
-    h.timer_start()
-    iters = []
+    iters, dev_ms = [], []
+    t0 = time.perf_counter()
     for _ in range(args.steps):
         iters.append(do_step(step)); step += 1
-    ms_total = h.timer_stop()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    c1 = h.counters()
-    # ---- timed region 2: end to end through the C ABI with host buffers ----
-    if restorable:
-        h.set_fields_raw(U_snap.data_ptr(), J_snap.data_ptr())
-        step = first_timed
-    barrier()
-    t0 = time.perf_counter()
-    iters2 = []
-    for _ in range(args.steps):
-        iters2.append(do_step(step)); step += 1
+        dev_ms.append(h.counters()["last_step_ms"])
         h.get_fields_raw(U_host.data_ptr(), J_host.data_ptr())
     torch.cuda.synchronize()
     e2e_ms_total = 1e3 * (time.perf_counter() - t0)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = h.counters()
+    ms_total = float(sum(dev_ms))
     tt = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -282,40 +270,45 @@ def main():
     ms_step = ms_total / args.steps
     e2e_step = e2e_ms_total / args.steps
 
-    # ---- roofline of the dominant kernel (rank 0's slab) ----
+    # ---- per-kernel roofline: every rank times its own slab, the slowest rank of each kernel is reported ----
     peak, peak_kind = measured_peak_gbs()
     n_own = h.n_owned
     nC_own = (h.k1 - h.k0) * p.sdx * p.sdy
-    ms_spmv2 = h.bench_kernel(1, 3, 20)
-    ms_spmv1 = h.bench_kernel(0, 3, 20)
-    ms_k3 = h.bench_kernel(2, 3, 20)
-    ms_k5 = h.bench_kernel(3, 3, 20)
-    ms_k6 = h.bench_kernel(4, 3, 20)
-    bytes_spmv2 = 16.0 * n_own + 5.0 * nC_own
-    ach = bytes_spmv2 / (ms_spmv2 * 1e-3) / 1e9
-    it_bytes = 152.0 * n_own + 10.0 * nC_own
+    kdefs = lib.KERNELS                      # (which, name, bytes per unknown, bytes per cell, reference lines)
+    mine = [h.bench_kernel(k[0], 3, 20) for k in kdefs] + [float(n_own), float(nC_own)]
+    tk = torch.tensor(mine, dtype=torch.float64, device="cuda")
+    if world > 1:
+        allk = [torch.zeros_like(tk) for _ in range(world)]
+        dist.all_gather(allk, tk)
+        allk = torch.stack(allk).cpu().numpy()
+    else:
+        allk = tk.cpu().numpy()[None, :]
     mean_it = float(np.mean(iters)) if iters else 0.0
     solve_ms_per_iter = (ms_total / max(sum(iters), 1))
-    kernels = {
-        "spmv_As_2dots": {"ms": ms_spmv2, "bytes": bytes_spmv2, "GBps": ach},
-        "spmv_Ap_dot": {"ms": ms_spmv1, "bytes": 24.0 * n_own + 5.0 * nC_own,
-                        "GBps": (24.0 * n_own + 5.0 * nC_own) / (ms_spmv1 * 1e-3) / 1e9},
-        "s_update_norm": {"ms": ms_k3, "bytes": 24.0 * n_own, "GBps": 24.0 * n_own / (ms_k3 * 1e-3) / 1e9},
-        "xr_update_2dots": {"ms": ms_k5, "bytes": 56.0 * n_own, "GBps": 56.0 * n_own / (ms_k5 * 1e-3) / 1e9},
-        "p_update": {"ms": ms_k6, "bytes": 32.0 * n_own, "GBps": 32.0 * n_own / (ms_k6 * 1e-3) / 1e9},
-    }
     if rank != 0:
         h.close()
         if world > 1:
             dist.destroy_process_group()
         return
-
-    traffic = None
+    kernels = {}
+    for q, (which, name, bpn, bpc, what) in enumerate(kdefs):
+        r = int(np.argmax(allk[:, q]))                       # the slowest rank sets the pace
+        ms_k, nn, cc = float(allk[r, q]), float(allk[r, -2]), float(allk[r, -1])
+        byt = bpn * nn + bpc * cc
+        kernels[name] = {"ms": ms_k, "bytes": byt, "GBps": byt / (ms_k * 1e-3) / 1e9, "frac": byt / (ms_k * 1e-3) / 1e9 / peak,
+                         "slowest_rank": r, "replaces": what}
+    it_bytes_rank0 = 152.0 * n_own + 10.0 * nC_own
+    # whole iteration against SURVEY 8d's UNCHANGED figure (19 passes + 2 map reads), slab of the largest rank
+    it_bytes = max(152.0 * float(a[-2]) + 10.0 * float(a[-1]) for a in allk)
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])         # dominant kernel = largest share of an iteration
+    kd = kernels[dom]
+    traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             tj = json.load(fh)
-        if world == 1 and str(grid) in tj and tj[str(grid)].get("k_spmv_tma<MODE_AS>"):
-            traffic = float(tj[str(grid)]["k_spmv_tma<MODE_AS>"])
+        if world == 1 and str(grid) in tj and tj[str(grid)].get(dom):
+            traffic = float(tj[str(grid)][dom])
+            traffic_src = "committed ncu --set full capture (profiles/ncu_traffic.json), not measured in this run"
     except Exception:
         traffic = None
     line = {
@@ -327,27 +320,35 @@ def main():
                    "grid": grid, "unknowns": n, "parallelism": f"zslab{world}",
                    "l2_policy": "inputs larger than L2 (every Krylov vector is %.1f GB per GPU)" % (8.0 * n_own / 1e9),
                    "iters_per_step": iters, "ms_per_iteration": solve_ms_per_iter,
+                   "timing": "value = sum of the per-step CUDA-event times recorded by ec3d_step on the library's "
+                             "stream (max over ranks); e2e = wall clock of the same steps incl. H2D scalars and "
+                             "D2H of the full fields after every step",
                    "create_s": t_create},
         "e2e": {"value": e2e_step, "unit": UNIT, "h2d_bytes_per_step": 8 * (p.numfun + p.numMech),
-                "d2h_bytes_per_step": 16 * n_own + 16, "iters_per_step": iters2,
-                "same_steps_as_value": bool(restorable)},
+                "d2h_bytes_per_step": 16 * n_own + 16, "iters_per_step": iters,
+                "same_steps_as_value": True},
         "gpu_launches": int(c1["launches"] - c0["launches"]),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": traffic, "peak_kind": peak_kind, "kernel": "k_spmv_tma<MODE_AS> (SpMV A*s fused with (As,s),(As,As))",
-                     "algorithmic_bytes": bytes_spmv2, "ms_per_launch": ms_spmv2},
+        "roofline": {"bound": "hbm", "achieved": kd["GBps"], "peak": peak, "unit": "GB/s", "frac": kd["frac"],
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+                     "kernel": f"{dom} ({kd['replaces']}) -- the kernel with the largest share of an iteration",
+                     "algorithmic_bytes": kd["bytes"], "ms_per_launch": kd["ms"], "slowest_rank": kd["slowest_rank"]},
         "roofline_iteration": {"bound": "hbm", "achieved": it_bytes / (solve_ms_per_iter * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s",
                                "frac": it_bytes / (solve_ms_per_iter * 1e-3) / 1e9 / peak,
-                               "algorithmic_bytes": it_bytes},
+                               "algorithmic_bytes": it_bytes,
+                               "note": "SURVEY 8d figure 152 n + 10 nC (19 vector passes + 2 map reads) of the largest slab "
+                                       "over the measured time per BiCGSTABwr iteration of the timed solves; the kernels "
+                                       "make fewer passes than that figure assumes (see DESIGN.md section 3)"},
         "kernels": kernels,
+        "sum_kernel_ms": float(sum(k["ms"] for k in kernels.values())),
     }
-    if args.record_iters and world == 1:
+    if world == 1:
         try:
             d = {}
             if os.path.exists(ITERS_FILE):
                 d = json.load(open(ITERS_FILE))
-            d[str(grid)] = {"mean_iters_per_step": float(np.mean(warm_iters + iters)),
+            d[str(grid) if args.variant == "A" else f"{grid}{args.variant}"] = {"mean_iters_per_step": float(np.mean(warm_iters + iters)),
                             "iters_by_step": warm_iters + iters, "warmup": args.warmup,
                             "source": "iteration counts of the GPU arm by timestep (deterministic; identical for 1/2/4/8 GPUs; "
                                       "equal to the oracle's where the oracle was run, see tests)"}

@@ -24,6 +24,17 @@ EXPORTS = [
 ]
 
 
+# ec3d_bench_kernel selectors of the kernels of one BiCGSTABwr iteration, in launch order:
+# (which, kernel, algorithmic bytes per owned unknown, per owned cell, what it replaces in solvers.f90)
+KERNELS = [
+    (0, "k_spmv_tma<AP>", 24.0, 5.0, "AP = A*P fused with (AP,R0), solvers.f90:30-32"),
+    (2, "k_s_update", 24.0, 0.0, "S = R - alpha*AP, ||S||^2, solvers.f90:33-34"),
+    (1, "k_spmv_tma<AS>", 16.0, 5.0, "AS = A*S fused with (AS,S), (AS,AS), solvers.f90:39-40"),
+    (3, "k_xr_update", 56.0, 0.0, "X += alpha*P + omega*S; R = S - omega*AS; ||R||^2; (R,R0), solvers.f90:41-44"),
+    (4, "k_p_update", 32.0, 0.0, "exit tests, beta, P = R + beta*(P - omega*AP), restart, solvers.f90:43-49"),
+]
+
+
 class Ec3dError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"ec3d_gpu error {code}: {msg}")
