@@ -58,8 +58,8 @@ struct SlabGeom {
     long long n_own;
     // global index (0-based, reference layout) of the first owned entry of each segment
     long long glob_off[4];
-    int vmap;                      // BLAS-1 kernels: 0 grid-stride, 1 one contiguous range per block
-    int vpad_;
+    int vmap;                      // generic BLAS-1 kernels: 0 grid-stride, 1 one contiguous range per block
+    int pad_;
 };
 
 // Local index of the U unknown of cell (i,j,k) (0-based global coordinates) in the dense U box.
@@ -74,7 +74,6 @@ struct Scal {
     double red_lo[8];              // low words of the per-rank double-double results (several ranks only)
     double rr0[2];                 // (R,R0), double-buffered by iteration parity
     double alpha, omega, beta;
-    double bnorm;
     double tol;
     int itmax;
     int done;                      // 1 once the solve has exited

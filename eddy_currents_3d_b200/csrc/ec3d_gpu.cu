@@ -25,6 +25,7 @@
 #include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------
@@ -146,14 +147,17 @@ struct Solver {
     int pstride = 0;
     double *X = nullptr, *R = nullptr, *R0 = nullptr, *P = nullptr, *AP = nullptr, *S = nullptr, *AS = nullptr;
     int nblkVec = 1, vec = 1;
+    bool fused_sas = false;                             // the SpMV has MODE_SAS (s-update fused into A*s)
+    bool ring = false;                                  // TMA-ring BLAS-1 kernels (needs vec == 2)
+    int nblkRingXR = 1, nblkRingP = 1, nblkRingS = 1;
     // launches the SpMV kernel(s) for `mode`; returns kernels launched
     std::function<int(int mode, const VecSet &vs, const IterCtl &ctl)> spmv;
-    std::function<int(double *v, int check_done)> halo; // refresh halo entries of v (nranks > 1)
+    std::function<int(double *v, double *v2, int check_done)> halo; // refresh halo entries of v (and v2) (nranks > 1)
     std::function<int(int slot, int count)> allreduce;  // sum sc->red[slot..slot+count) over ranks
     bool multi = false;
     bool p2p = false;                                   // exchanges are plain kernels: graph capture allowed
     bool x_halo_fresh = false;                          // the caller just exchanged the halo of X
-    // graph of `graph_chunk` iterations (single rank only)
+    // graph of `graph_chunk` iterations
     cudaGraphExec_t graph = nullptr;
     int graph_chunk = 0;
     long long graph_launches = 0;                       // kernels inside one graph launch
@@ -164,33 +168,93 @@ struct Solver {
     int predicted = 0;                                  // iteration count of the previous solve
 };
 
-static int solver_enqueue_iteration(Solver &s, int it_off)
+static VecSet vecset_ap(const Solver &s) { return VecSet{s.P, s.AP, s.R0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; }
+static VecSet vecset_as(const Solver &s) { return VecSet{s.S, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; }
+static VecSet vecset_sas(const Solver &s) { return VecSet{s.R, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr, s.AP, s.S}; }
+
+static void launch_s_update(Solver &s, const IterCtl &ctl)
 {
     const SlabGeom &G = s.G;
+    if (s.ring) {
+        const unsigned nb = (unsigned)s.nblkRingS;
+        k_s_update_tma<<<nb, 256, v1_smem_bytes(2, S_NST), s.st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
+    } else {
+        const unsigned nb = (unsigned)s.nblkVec;
+        if (s.vec == 2) k_s_update<2><<<nb, 256, 0, s.st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
+        else            k_s_update<1><<<nb, 256, 0, s.st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
+    }
+    LAUNCHED(s.launches);
+}
+static void launch_xr_update(Solver &s, double *X, const IterCtl &ctl)
+{
+    const SlabGeom &G = s.G;
+    if (s.ring) {
+        const unsigned nb = (unsigned)s.nblkRingXR;
+        k_xr_update_tma<<<nb, 256, v1_smem_bytes(5, XR_NST), s.st>>>(G, X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
+    } else {
+        const unsigned nb = (unsigned)s.nblkVec;
+        if (s.vec == 2) k_xr_update<2><<<nb, 256, 0, s.st>>>(G, X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
+        else            k_xr_update<1><<<nb, 256, 0, s.st>>>(G, X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
+    }
+    LAUNCHED(s.launches);
+}
+static void launch_p_update(Solver &s, const IterCtl &ctl)
+{
+    const SlabGeom &G = s.G;
+    if (s.ring) {
+        k_p_update_tma<<<(unsigned)s.nblkRingP, 256, v1_smem_bytes(3, P_NST), s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
+    } else {
+        const unsigned nb = (unsigned)s.nblkVec;
+        if (s.vec == 2) k_p_update<2><<<nb, 256, 0, s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
+        else            k_p_update<1><<<nb, 256, 0, s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
+    }
+    LAUNCHED(s.launches);
+}
+
+// One BiCGSTABwr iteration (solvers.f90:29-49).  Matrix-free TMA path: 4 kernels, 3 reduction points,
+// 18 vector passes (s = r - alpha*Ap lives inside the A*s SpMV); generic / CSR path: 5 kernels.
+static int solver_enqueue_iteration(Solver &s, int it_off)
+{
     const IterCtl ctl{s.sc, s.iter_base, it_off};
-    const unsigned nb = (unsigned)s.nblkVec;
-    if (s.multi) { int rc = s.halo(s.P, 1); if (rc) return rc; }
-    {   // AP = A*P, (AP,R0)                                        solvers.f90:30-32
-        VecSet vs{s.P, s.AP, s.R0, nullptr, nullptr, nullptr, nullptr};
-        s.launches += s.spmv(MODE_AP, vs, ctl);
-    }
+    if (s.multi) { int rc = s.halo(s.P, nullptr, 1); if (rc) return rc; }
+    s.launches += s.spmv(MODE_AP, vecset_ap(s), ctl);                 // AP = A*P, (AP,R0)      solvers.f90:30-32
     if (s.multi) { int rc = s.allreduce(RED_APR0, 1); if (rc) return rc; }
-    if (s.vec == 2) k_s_update<2><<<nb, 256, 0, s.st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
-    else            k_s_update<1><<<nb, 256, 0, s.st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
-    LAUNCHED(s.launches);
-    if (s.multi) { int rc = s.allreduce(RED_SS, 1); if (rc) return rc; rc = s.halo(s.S, 1); if (rc) return rc; }
-    {   // AS = A*S, (AS,S), (AS,AS)                                solvers.f90:39-40
-        VecSet vs{s.S, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr};
-        s.launches += s.spmv(MODE_AS, vs, ctl);
+    if (s.fused_sas) {
+        if (s.multi) { int rc = s.halo(s.R, s.AP, 1); if (rc) return rc; }
+        // S = R - alpha*AP; AS = A*S; ||S||^2, (AS,S), (AS,AS)        solvers.f90:33-40 (AS is speculative:
+        // when ||S|| passes the test of :34 the x-update below takes the exit and AS is never used)
+        s.launches += s.spmv(MODE_SAS, vecset_sas(s), ctl);
+        if (s.multi) { int rc = s.allreduce(RED_SS, 3); if (rc) return rc; }
+    } else {
+        launch_s_update(s, ctl);
+        if (s.multi) { int rc = s.allreduce(RED_SS, 1); if (rc) return rc; rc = s.halo(s.S, nullptr, 1); if (rc) return rc; }
+        s.launches += s.spmv(MODE_AS, vecset_as(s), ctl);             // AS = A*S, (AS,S), (AS,AS)  solvers.f90:39-40
+        if (s.multi) { int rc = s.allreduce(RED_ASS, 2); if (rc) return rc; }
     }
-    if (s.multi) { int rc = s.allreduce(RED_ASS, 2); if (rc) return rc; }
-    if (s.vec == 2) k_xr_update<2><<<nb, 256, 0, s.st>>>(G, s.X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
-    else            k_xr_update<1><<<nb, 256, 0, s.st>>>(G, s.X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
-    LAUNCHED(s.launches);
+    launch_xr_update(s, s.X, ctl);
     if (s.multi) { int rc = s.allreduce(RED_RR, 2); if (rc) return rc; }
-    if (s.vec == 2) k_p_update<2><<<nb, 256, 0, s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
-    else            k_p_update<1><<<nb, 256, 0, s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
-    LAUNCHED(s.launches);
+    launch_p_update(s, ctl);
+    return EC3D_OK;
+}
+
+static int solver_setup_ring(Solver &s)
+{
+    const char *er = getenv("EC3D_RING");
+    s.ring = (s.vec == 2) && !(er && atoi(er) == 0);
+    if (!s.ring) return EC3D_OK;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(k_xr_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, v1_smem_bytes(5, XR_NST)));
+        CUDA_TRY(cudaFuncSetAttribute(k_p_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, v1_smem_bytes(3, P_NST)));
+        CUDA_TRY(cudaFuncSetAttribute(k_s_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, v1_smem_bytes(2, S_NST)));
+        attr_done = true;
+    }
+    long long nch = 0;
+    for (int c = 0; c < 4; ++c) nch += (s.G.own_len[c] + V1_CH - 1) / V1_CH;
+    nch = std::max<long long>(nch, 1);
+    s.nblkRingXR = (int)std::min<long long>(nch, 148);          // 1 CTA / SM (3 stages x 40 KB)
+    s.nblkRingP = (int)std::min<long long>(nch, 148 * 2);       // 2 CTAs / SM (4 stages x 24 KB)
+    s.nblkRingS = (int)std::min<long long>(nch, 148 * 2);
     return EC3D_OK;
 }
 
@@ -201,9 +265,18 @@ static int solver_build_graph(Solver &s, int chunk)
     const long long before = s.launches;
     const long long gbefore = g_launches.load();
     CUDA_TRY(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
-    for (int q = 1; q <= chunk; ++q) solver_enqueue_iteration(s, q);
+    int erc = EC3D_OK;
+    for (int q = 1; q <= chunk && erc == EC3D_OK; ++q) erc = solver_enqueue_iteration(s, q);
     k_iter_advance<<<1, 1, 0, s.st>>>(s.iter_base, chunk);
-    CUDA_TRY(cudaStreamEndCapture(s.st, &g));
+    const cudaError_t ce = cudaStreamEndCapture(s.st, &g);   // always leave capture mode, also on errors
+    if (erc != EC3D_OK || ce != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        s.launches = before;
+        g_launches.store(gbefore);
+        if (erc != EC3D_OK) return erc;
+        ec3d_set_error("graph capture of the iteration failed: %s", cudaGetErrorString(ce));
+        return EC3D_ERR_CUDA;
+    }
     CUDA_TRY(cudaGraphInstantiate(&s.graph, g, 0));
     CUDA_TRY(cudaGraphDestroy(g));
     s.graph_chunk = chunk;
@@ -218,10 +291,10 @@ static int solver_run(Solver &s, const double *B, double tol, int itmax, int *it
 {
     k_solver_reset<<<1, 1, 0, s.st>>>(s.sc, s.iter_base, tol, itmax, s.multi ? 1 : 0);
     LAUNCHED(s.launches);
-    if (s.multi && !s.x_halo_fresh) { int rc = s.halo(s.X, 0); if (rc) return rc; }
+    if (s.multi && !s.x_halo_fresh) { int rc = s.halo(s.X, nullptr, 0); if (rc) return rc; }
     s.x_halo_fresh = false;
     {   // R = B - A*X; R0 = R; P = R; ||b||^2; (R,R0)               solvers.f90:13-21
-        VecSet vs{s.X, nullptr, nullptr, B, s.R, s.R0, s.P};
+        VecSet vs{s.X, nullptr, nullptr, B, s.R, s.R0, s.P, nullptr, nullptr};
         const IterCtl ctl{s.sc, s.iter_base, 0};
         s.launches += s.spmv(MODE_INIT, vs, ctl);
     }
@@ -268,6 +341,18 @@ static int solver_run(Solver &s, const double *B, double tol, int itmax, int *it
     return EC3D_OK;
 }
 
+// Stride (doubles) between consecutive vectors of one allocation: the natural length rounded up to a
+// 2 MiB multiple plus 1 MiB + 4 KiB.  Vectors whose bases differ by large powers of two make the 5-7
+// streams of a BLAS-1 kernel collide in the L2-slice / DRAM-channel hash (scripts/stream_probe.cu:
+// 0.84 -> 0.985 of the copy peak for grid-stride loads on 3.4 GB vectors); EC3D_VPAD=<doubles> overrides.
+static long long padded_stride(long long len)
+{
+    const char *ep = getenv("EC3D_VPAD");
+    if (ep) { long long v = len + atoll(ep); return v + (v & 1); }
+    const long long two_mib = (2LL << 20) / 8;
+    return (len + two_mib - 1) / two_mib * two_mib + ((1LL << 20) + 4096) / 8;
+}
+
 static void flat_geom(long long n, SlabGeom &G)
 {
     memset(&G, 0, sizeof(G));
@@ -286,11 +371,49 @@ static int vec_blocks(long long n_own, int vec)
 // ------------------------------------------------------------------------------------------
 // 1. strict drop-in: CSR BiCGSTABwr with a cached device copy of the matrix
 // ------------------------------------------------------------------------------------------
+// 64-bit content hash (word-wise multiply-xorshift), chunks hashed by up to 8 host threads and
+// combined in chunk order.  One pass over irow, jcol and valA costs far less than the solve the
+// arrays are about to be used for, and it is what makes the device copy safe to reuse: a host that
+// re-assembles into the same arrays (new dt / sigma) or frees and reallocates them at the same
+// address gets a fresh upload instead of a stale matrix.
+static uint64_t hash_words(const void *p, size_t bytes, uint64_t seed)
+{
+    const unsigned char *b = static_cast<const unsigned char *>(p);
+    uint64_t h = seed ^ (bytes * 0x9E3779B97F4A7C15ull);
+    size_t q = 0;
+    for (; q + 8 <= bytes; q += 8) {
+        uint64_t w;
+        memcpy(&w, b + q, 8);
+        h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+        h ^= h >> 32;
+    }
+    uint64_t w = 0;
+    if (q < bytes) { memcpy(&w, b + q, bytes - q); h = (h ^ w) * 0xD6E8FEB86659FD93ull; h ^= h >> 32; }
+    return h;
+}
+static uint64_t hash_array(const void *p, size_t bytes, uint64_t seed)
+{
+    const size_t min_chunk = (size_t)8 << 20;
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>(8, bytes / min_chunk));
+    if (nt == 1) return hash_words(p, bytes, seed);
+    std::vector<uint64_t> part(nt);
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nt) + 7) & ~(size_t)7;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t] {
+            const size_t a = std::min(bytes, per * t), e = (t == nt - 1) ? bytes : std::min(bytes, per * (t + 1));
+            part[t] = hash_words(static_cast<const unsigned char *>(p) + a, e - a, seed + t);
+        });
+    for (auto &x : th) x.join();
+    return hash_words(part.data(), part.size() * sizeof(uint64_t), seed);
+}
+
 struct CsrCache {
     const void *hval = nullptr, *hirow = nullptr, *hjcol = nullptr;
-    int n = 0; long long nnz = 0; int first_irow = 0, last_jcol = 0; double first_val = 0.0;
+    int n = 0; long long nnz = 0; uint64_t fp_irow = 0, fp_jcol = 0, fp_val = 0;
     int *irow = nullptr, *jcol = nullptr; double *val = nullptr;
-    double *vecs = nullptr;     // 8 vectors of n: X,B,R,R0,P,AP,S,AS
+    double *vecs = nullptr;     // 8 vectors of n (stride vstride): X,B,R,R0,P,AP,S,AS
+    long long vstride = 0;
     Solver sol;
     cudaStream_t st = nullptr;
     bool ready = false;
@@ -317,19 +440,30 @@ extern "C" void ec3d_csr_cache_clear(void)
 static int csr_prepare(const double *valA, const int32_t *irow, const int32_t *jcol, int32_t n)
 {
     const long long nnz = (long long)irow[n] - 1;
+    if (irow[0] != 1 || nnz < 0) { ec3d_set_error("irow is not a 1-based CSR row pointer"); return EC3D_ERR_ARG; }
     CsrCache &c = g_csr;
-    if (c.ready && c.hval == valA && c.hirow == irow && c.hjcol == jcol && c.n == n && c.nnz == nnz &&
-        c.first_irow == irow[1] && c.last_jcol == jcol[nnz - 1] && c.first_val == valA[0])
+    const uint64_t fi = hash_array(irow, (size_t)(n + 1) * sizeof(int32_t), 1);
+    const uint64_t fj = hash_array(jcol, (size_t)nnz * sizeof(int32_t), 2);
+    const uint64_t fv = hash_array(valA, (size_t)nnz * sizeof(double), 3);
+    if (c.ready && c.n == n && c.nnz == nnz && c.fp_irow == fi && c.fp_jcol == fj && c.fp_val == fv)
+        return EC3D_OK;                                   // same CONTENTS: the device copy is valid
+    if (c.ready && c.n == n && c.nnz == nnz && c.fp_irow == fi && c.fp_jcol == fj) {
+        // same sparsity, new values (re-assembly with another dt / sigma): refresh valA only
+        CUDA_TRY(cudaMemcpyAsync(c.val, valA, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, c.st));
+        CUDA_TRY(cudaStreamSynchronize(c.st));
+        c.fp_val = fv; c.hval = valA; c.hirow = irow; c.hjcol = jcol;
         return EC3D_OK;
+    }
     if (c.ready || c.irow) c.release();
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (ndev < 1) { ec3d_set_error("no CUDA device"); return EC3D_ERR_CUDA; }
     CUDA_TRY(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&c.irow, (size_t)(n + 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&c.jcol, (size_t)nnz * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&c.val, (size_t)nnz * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&c.vecs, (size_t)n * 8 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c.jcol, (size_t)std::max<long long>(nnz, 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c.val, (size_t)std::max<long long>(nnz, 1) * sizeof(double)));
+    const long long vstride = padded_stride(n);
+    CUDA_TRY(cudaMalloc(&c.vecs, (size_t)vstride * 8 * sizeof(double)));
     CUDA_TRY(cudaMemcpyAsync(c.irow, irow, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, c.st));
     CUDA_TRY(cudaMemcpyAsync(c.jcol, jcol, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, c.st));
     CUDA_TRY(cudaMemcpyAsync(c.val, valA, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, c.st));
@@ -341,12 +475,14 @@ static int csr_prepare(const double *valA, const int32_t *irow, const int32_t *j
     const int nblk = (n + 255) / 256;
     s.vec = (n % 2 == 0) ? 2 : 1;
     s.nblkVec = vec_blocks(n, s.vec);
-    s.pstride = std::max(nblk, s.nblkVec);
-    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 4 * sizeof(double)));
+    { int rc = solver_setup_ring(s); if (rc) return rc; }
+    s.pstride = std::max(std::max(nblk, s.nblkVec), 2 * 148) + 8;
+    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 6 * sizeof(double)));
     CUDA_TRY(cudaHostAlloc(&s.h_flags, 4 * sizeof(int), cudaHostAllocDefault));
     double *v = c.vecs;
-    s.X = v; s.R = v + 2LL * n; s.R0 = v + 3LL * n; s.P = v + 4LL * n; s.AP = v + 5LL * n; s.S = v + 6LL * n;
-    s.AS = v + 7LL * n;
+    c.vstride = vstride;
+    s.X = v; s.R = v + 2 * vstride; s.R0 = v + 3 * vstride; s.P = v + 4 * vstride; s.AP = v + 5 * vstride;
+    s.S = v + 6 * vstride; s.AS = v + 7 * vstride;
     const int *dirow = c.irow, *djcol = c.jcol;
     const double *dval = c.val;
     Solver *sp = &s;
@@ -365,7 +501,7 @@ static int csr_prepare(const double *valA, const int32_t *irow, const int32_t *j
     const char *ge = getenv("EC3D_GRAPH");
     if (!ge || atoi(ge) != 0) { int rc = solver_build_graph(s, 8); if (rc) return rc; }
     c.hval = valA; c.hirow = irow; c.hjcol = jcol; c.n = n; c.nnz = nnz;
-    c.first_irow = irow[1]; c.last_jcol = jcol[nnz - 1]; c.first_val = valA[0];
+    c.fp_irow = fi; c.fp_jcol = fj; c.fp_val = fv;
     c.ready = true;
     return EC3D_OK;
 }
@@ -379,7 +515,7 @@ extern "C" int ec3d_bicgstabwr_csr(const double *valA, const int32_t *irow, cons
     if (rc) return rc;
     CsrCache &c = g_csr;
     Solver &s = c.sol;
-    double *dB = c.vecs + (long long)n;
+    double *dB = c.vecs + c.vstride;
     CUDA_TRY(cudaMemcpyAsync(s.X, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.st));
     CUDA_TRY(cudaMemcpyAsync(dB, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.st));
     rc = solver_run(s, dB, tolerance, itmax, iter);
@@ -394,9 +530,19 @@ extern "C" void sprsbcgstabwr_(double *valA, int32_t *irow, int32_t *jcol, int32
 {
     int rc = ec3d_bicgstabwr_csr(valA, irow, jcol, *n, b, x, *tolerance, *itmax, iter);
     if (rc != EC3D_OK) {
+        // the reference's interface has no status argument and its host ignores iter (EC3D.f90:408):
+        // returning would let the time loop continue on a stale x, so stop like a Fortran STOP would
         fprintf(stderr, "sprsbcgstabwr_ (GPU): error %d: %s\n", rc, ec3d_last_error());
+        fflush(stderr);
         *iter = -1;
+        if (!getenv("EC3D_NO_ABORT")) abort();
     }
+}
+// ifort / Windows mangling of the same external procedure (reference Makefile:30-47): upper case, no underscore
+extern "C" void SPRSBCGSTABWR(double *valA, int32_t *irow, int32_t *jcol, int32_t *n, double *b, double *x,
+                              double *tolerance, int32_t *itmax, int32_t *iter)
+{
+    sprsbcgstabwr_(valA, irow, jcol, n, b, x, tolerance, itmax, iter);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -420,7 +566,8 @@ struct ec3d_handle {
     int mat0 = 0;
     MatCoef mc0{};
     bool tma = false;                    // k_spmv_tma usable (even sdx); else k_air_spmv + k_cond_spmv
-    int nstage = 0;                      // depth of the TMA ring forced by EC3D_NSTAGE = 3, 4, 5 (0: per mode)
+    int ccps = 2;                        // CTAs per SM of the conductor-item kernel (EC3D_CCPS = 1 | 2)
+    int nitems_cond = 0, nitems_lean = 0;// d_items = [conductor items | lean items]
     CUtensorMap tmA[EC3D_NVEC], tmU[EC3D_NVEC];   // per local vector: A part (4-D), dense U box (3-D)
     CUtensorMap tmPA[EC3D_NVEC], tmPU[EC3D_NVEC]; // same tensors with halo-free 64 x 8 boxes (L2 prefetch of r0 / b)
     CUtensorMap tmC;                     // class bytes (3-D, uint8)
@@ -459,7 +606,7 @@ struct ec3d_handle {
     PeerTable pt{};
     CommBlock *d_cb = nullptr;
     CommLocal *d_cl = nullptr;
-    double *d_gather = nullptr;              // NCCL path: [nranks][4] gathered double-double partials
+    double *d_gather = nullptr;              // NCCL path: [nranks][RED_W] gathered double-double partials
     void *ipc_vecs_lo = nullptr, *ipc_vecs_hi = nullptr;
     void *ipc_cb[EC3D_MAX_RANKS] = {nullptr};
     const double *halo_fresh = nullptr;      // vector whose halo was exchanged last and not modified since
@@ -471,21 +618,10 @@ struct ec3d_handle {
     long long launches = 0;
 };
 
-static int h_halo(ec3d_handle *h, double *v, int check_done = 0)
+static int h_halo_nccl_one(ec3d_handle *h, double *v)
 {
-    if (h->nranks == 1) return EC3D_OK;
     const SlabGeom &G = h->G;
     const long long kdz = G.kdz;
-    if (h->p2p) {
-        const int vidx = (int)((v - h->vecs) / G.ltot);
-        const long long work = 3 * kdz / 2 + std::max(h->nU_send_lo, h->nU_send_hi);
-        const int nb = (int)std::max<long long>(1, std::min<long long>((work + 255) / 256, 148 * 4));
-        k_halo_push<<<nb, 256, 0, h->st>>>(G, h->pt, h->vecs, vidx, h->nU_send_lo, h->nU_send_hi, h->sol.sc, check_done, h->d_cl);
-        k_halo_wait<<<1, 32, 0, h->st>>>(h->pt, h->sol.sc, check_done, h->d_cl);
-        h->launches += 2; g_launches.fetch_add(2);
-        return EC3D_OK;
-    }
-    NCCL_TRY(ncclGroupStart());
     if (h->rank > 0) {
         const int peer = h->rank - 1;
         for (int c = 0; c < 3; ++c) {
@@ -505,8 +641,30 @@ static int h_halo(ec3d_handle *h, double *v, int check_done = 0)
             NCCL_TRY(ncclSend(v + G.offU + G.nUlo + G.nUown - h->nU_send_hi, h->nU_send_hi, ncclDouble, peer, h->comm, h->st));
         if (G.nUhi) NCCL_TRY(ncclRecv(v + G.offU + G.nUlo + G.nUown, G.nUhi, ncclDouble, peer, h->comm, h->st));
     }
-    NCCL_TRY(ncclGroupEnd());
     return EC3D_OK;
+}
+
+// Refreshes the halo entries of local vector v (and of v2 when given: the fused A*s SpMV reads r AND Ap).
+static int h_halo(ec3d_handle *h, double *v, double *v2 = nullptr, int check_done = 0)
+{
+    if (h->nranks == 1) return EC3D_OK;
+    const SlabGeom &G = h->G;
+    const long long kdz = G.kdz;
+    if (h->p2p) {
+        const int vidx = (int)((v - h->vecs) / G.ltot);
+        const int vidx2 = v2 ? (int)((v2 - h->vecs) / G.ltot) : -1;
+        const long long work = 3 * kdz / 2 + std::max(h->nU_send_lo, h->nU_send_hi);
+        const int nb = (int)std::max<long long>(1, std::min<long long>((work + 255) / 256, 148 * 4));
+        k_halo_push<<<nb, 256, 0, h->st>>>(G, h->pt, h->vecs, vidx, vidx2, h->nU_send_lo, h->nU_send_hi, h->sol.sc, check_done, h->d_cl);
+        k_halo_wait<<<1, 32, 0, h->st>>>(h->pt, h->sol.sc, check_done, h->d_cl);
+        h->launches += 2; g_launches.fetch_add(2);
+        return EC3D_OK;
+    }
+    NCCL_TRY(ncclGroupStart());
+    int rc = h_halo_nccl_one(h, v);
+    if (!rc && v2) rc = h_halo_nccl_one(h, v2);
+    NCCL_TRY(ncclGroupEnd());
+    return rc;
 }
 
 static int h_allreduce(ec3d_handle *h, int slot, int count)
@@ -518,8 +676,8 @@ static int h_allreduce(ec3d_handle *h, int slot, int count)
         return EC3D_OK;
     }
     // NCCL path: gather every rank's double-double partial(s), sum them in rank order on every rank
-    k_red_pack<<<1, 32, 0, h->st>>>(h->sol.sc, slot, count, h->d_gather + 4 * h->rank);
-    NCCL_TRY(ncclAllGather(h->d_gather + 4 * h->rank, h->d_gather, 4, ncclDouble, h->comm, h->st));
+    k_red_pack<<<1, 32, 0, h->st>>>(h->sol.sc, slot, count, h->d_gather + RED_W * h->rank);
+    NCCL_TRY(ncclAllGather(h->d_gather + RED_W * h->rank, h->d_gather, RED_W, ncclDouble, h->comm, h->st));
     k_red_unpack<<<1, 32, 0, h->st>>>(h->sol.sc, slot, count, h->d_gather, h->nranks);
     h->launches += 2; g_launches.fetch_add(2);
     return EC3D_OK;
@@ -527,13 +685,25 @@ static int h_allreduce(ec3d_handle *h, int slot, int count)
 
 static int scan_i32_to_i64(cudaStream_t st, const int *in, long long *out, long long n, long long *total_host, long long &launches);
 
-template <int MODE, int NSTAGE>
-static void launch_tma(ec3d_handle *h, int v, int vaux, const VecSet &vs, const IterCtl &ctl)
+// Ring depth per (mode, item kind, CTAs per SM).  Lean items (no conductor cells): 2 CTAs / SM; the
+// modes that also stream r0 / b through L1 (AP, INIT) measure faster with 3 stages (more of the 228 KB
+// left as L1), PLAIN with 4; MODE_SAS stages two inputs (32 KB per stage).  Conductor items: EC3D_CCPS
+// selects 2 CTAs / SM (128 registers) or 1 CTA / SM (255 registers, no spills, deeper ring).
+template <int MODE> struct RingCfg {
+    static constexpr int LEAN = (MODE == MODE_PLAIN) ? 4 : 3;
+    static constexpr int COND2 = (MODE == MODE_SAS) ? 2 : (MODE == MODE_PLAIN) ? 4 : 3;
+    static constexpr int COND1 = (MODE == MODE_SAS) ? 4 : (MODE == MODE_PLAIN) ? 8 : 6;
+};
+
+template <int MODE, int NSTAGE, bool HAS_U, int CPS>
+static void launch_tma_kind(ec3d_handle *h, const TmaMaps &tm, const WorkItem *items, int nitems, int pbase, unsigned expected,
+                            const VecSet &vs, const IterCtl &ctl)
 {
+    if (nitems <= 0) return;
     Solver &s = h->sol;
-    k_spmv_tma<MODE, NSTAGE><<<h->airGrid, dim3(32, 8), tma::smem_bytes(NSTAGE), h->st>>>(
-        h->tmA[v], h->tmU[v], h->tmC, h->tmPA[vaux], h->tmPU[vaux], h->G, h->cf, h->mc0, h->d_items, vs, ctl, s.partials,
-        s.pstride, (unsigned)h->nblkAir, 1);
+    k_spmv_tma<MODE, NSTAGE, HAS_U, CPS><<<nitems, dim3(32, 8), tma_smem_bytes<MODE, HAS_U>(NSTAGE), h->st>>>(
+        tm, h->G, h->cf, h->mc0, items, vs, ctl, s.partials, s.pstride, pbase, expected);
+    g_launches.fetch_add(1);
 }
 
 template <int MODE>
@@ -541,23 +711,31 @@ static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
 {
     Solver &s = h->sol;
     if (h->tma) {
-        // main path: one TMA-staged kernel produces every row (ec3d_tma.cuh)
+        // main path: TMA-staged kernels produce every row (ec3d_tma.cuh): conductor items first, then lean items
         const long long v = (vs.x - h->vecs) / h->G.ltot;
         if (v < 0 || v >= EC3D_NVEC || h->vecs + v * h->G.ltot != vs.x) { ec3d_set_error("SpMV input is not a handle vector"); return -1; }
-        const double *auxp = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : vs.x;
+        const double *auxp = (MODE == MODE_AP) ? vs.r0 : (MODE == MODE_INIT) ? vs.b : (MODE == MODE_SAS) ? vs.x2 : vs.x;
         long long va = (auxp - h->vecs) / h->G.ltot;
-        if (va < 0 || va >= EC3D_NVEC) va = v;            // (only used for an L2 prefetch)
-        // ring depth: the modes that also stream r0 / b through L1 (AP, INIT) measure faster with 3 stages
-        // (more of the 228 KB left as L1), the pure-TMA modes with 4; EC3D_NSTAGE overrides both
-        const int ns = h->nstage ? h->nstage : ((MODE == MODE_AP || MODE == MODE_INIT) ? 3 : 4);
-        switch (ns) {
-        case 3: launch_tma<MODE, 3>(h, (int)v, (int)va, vs, ctl); break;
-        case 5: launch_tma<MODE, 5>(h, (int)v, (int)va, vs, ctl); break;
-        default: launch_tma<MODE, 4>(h, (int)v, (int)va, vs, ctl); break;
+        if (va < 0 || va >= EC3D_NVEC) va = v;            // (AP / INIT: only used for an L2 prefetch)
+        TmaMaps tm;
+        tm.xA = h->tmA[v]; tm.xU = h->tmU[v];
+        tm.x2A = h->tmA[va]; tm.x2U = h->tmU[va];
+        tm.cls = h->tmC;
+        tm.auxA = h->tmPA[va]; tm.auxU = h->tmPU[va];
+        const unsigned expected = (unsigned)(h->nitems_cond + h->nitems_lean);
+        int nl = 0;
+        if (h->nitems_cond) {
+            if (h->ccps == 1) launch_tma_kind<MODE, RingCfg<MODE>::COND1, true, 1>(h, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
+            else              launch_tma_kind<MODE, RingCfg<MODE>::COND2, true, 2>(h, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
+            ++nl;
         }
-        g_launches.fetch_add(1);
-        return 1;
+        if (h->nitems_lean) {
+            launch_tma_kind<MODE, RingCfg<MODE>::LEAN, false, 2>(h, tm, h->d_items + h->nitems_cond, h->nitems_lean, h->nitems_cond, expected, vs, ctl);
+            ++nl;
+        }
+        return nl;
     }
+    if (MODE == MODE_SAS) { ec3d_set_error("MODE_SAS needs the TMA SpMV"); return -1; }
     // generic path (odd sdx): 7-point kernel for non-conductor cells + list kernel for conductor cells
     const unsigned expected = (unsigned)(h->nblkAir + h->nblkCond);
     k_air_spmv<MODE, 32, 8><<<h->airGrid, dim3(32, 8), 0, h->st>>>(h->G, h->cf, h->d_geo, vs, ctl, h->zc, s.partials,
@@ -576,6 +754,7 @@ static int h_spmv(ec3d_handle *h, int mode, const VecSet &vs, const IterCtl &ctl
     case MODE_AP:   return launch_stencil<MODE_AP>(h, vs, ctl);
     case MODE_AS:   return launch_stencil<MODE_AS>(h, vs, ctl);
     case MODE_INIT: return launch_stencil<MODE_INIT>(h, vs, ctl);
+    case MODE_SAS:  return launch_stencil<MODE_SAS>(h, vs, ctl);
     default:        return launch_stencil<MODE_PLAIN>(h, vs, ctl);
     }
 }
@@ -727,7 +906,7 @@ static int setup_p2p(ec3d_handle *h, bool want)
     const SlabGeom &G = h->G;
     CUDA_TRY(cudaMalloc(&h->d_cb, sizeof(CommBlock)));
     CUDA_TRY(cudaMalloc(&h->d_cl, sizeof(CommLocal)));
-    CUDA_TRY(cudaMalloc(&h->d_gather, (size_t)nr * 4 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->d_gather, (size_t)nr * RED_W * sizeof(double)));
     CUDA_TRY(cudaMemset(h->d_cb, 0, sizeof(CommBlock)));
     CUDA_TRY(cudaMemset(h->d_cl, 0, sizeof(CommLocal)));
     P2pXchg mine;
@@ -850,25 +1029,24 @@ static int encode_tensor_maps(ec3d_handle *h)
     return EC3D_OK;
 }
 
-template <int MODE, int NSTAGE>
-static cudaError_t set_attr_one()
-{
-    return cudaFuncSetAttribute(k_spmv_tma<MODE, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::smem_bytes(NSTAGE));
-}
-template <int NSTAGE>
-static cudaError_t set_attr_modes()
+template <int MODE>
+static cudaError_t set_attr_mode()
 {
     cudaError_t e;
-    if ((e = set_attr_one<MODE_PLAIN, NSTAGE>()) != cudaSuccess) return e;
-    if ((e = set_attr_one<MODE_AP, NSTAGE>()) != cudaSuccess) return e;
-    if ((e = set_attr_one<MODE_AS, NSTAGE>()) != cudaSuccess) return e;
-    return set_attr_one<MODE_INIT, NSTAGE>();
+    using RC = RingCfg<MODE>;
+    if ((e = cudaFuncSetAttribute(k_spmv_tma<MODE, RC::LEAN, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tma_smem_bytes<MODE, false>(RC::LEAN))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_spmv_tma<MODE, RC::COND2, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tma_smem_bytes<MODE, true>(RC::COND2))) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_spmv_tma<MODE, RC::COND1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                tma_smem_bytes<MODE, true>(RC::COND1));
 }
 static int set_tma_smem_attr()
 {
-    CUDA_TRY(set_attr_modes<3>());
-    CUDA_TRY(set_attr_modes<4>());
-    CUDA_TRY(set_attr_modes<5>());
+    CUDA_TRY(set_attr_mode<MODE_PLAIN>());
+    CUDA_TRY(set_attr_mode<MODE_AP>());
+    CUDA_TRY(set_attr_mode<MODE_INIT>());
+    CUDA_TRY(set_attr_mode<MODE_SAS>());
     return EC3D_OK;
 }
 
@@ -902,7 +1080,11 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
 
     // ---- slab partition ----
     std::vector<long long> cpp(sdz, 0);          // conductor cells per plane
-    for (long long q = 0; q < Nc; ++q) cpp[(cfg->cond_nod[q] - 1) / kdz]++;
+    for (long long q = 0; q < Nc; ++q) {
+        const long long c0 = (long long)cfg->cond_nod[q] - 1;
+        if (c0 < 0 || c0 >= nC) { ec3d_set_error("conductor cell number out of range"); return EC3D_ERR_ARG; }
+        cpp[c0 / kdz]++;
+    }
     std::vector<int> kstart(h->nranks + 1, 0);
     {
         std::vector<int64_t> cpp64(cpp.begin(), cpp.end());
@@ -938,16 +1120,16 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     h->nU_send_lo = ucum(G.k0 + 2) - u_own0;
     h->nU_send_hi = u_own1 - ucum(G.k1 - 2);
     long long segA = (long long)(G.nzl + 2) * kdz;
+    {
+        // EC3D_SEGPAD=<doubles>: extra distance between the Ax / Ay / Az segments of a vector (the three
+        // component tiles of one TMA box are segA apart; on 2^k grids that is a large power of two)
+        const char *es = getenv("EC3D_SEGPAD");
+        if (es) segA += atoll(es);
+    }
     segA += segA & 1;
     G.segA = segA; G.offU = 3 * segA;
-    G.ltot = G.offU + G.nUlo + G.nUown + G.nUhi + 2;
-    {
-        // vectors are laid out back to back; an odd multiple of 4 KiB between them keeps the 5-7 streams
-        // of a BLAS-1 kernel from sitting at the same offset of a DRAM page / bank (EC3D_VPAD overrides)
-        const char *ep = getenv("EC3D_VPAD");
-        const long long pad = ep ? atoll(ep) : 0;
-        G.ltot += pad;
-    }
+    // vectors are laid out back to back with a de-aliasing stride, see padded_stride()
+    G.ltot = padded_stride(G.offU + G.nUlo + G.nUown + G.nUhi + 2);
     G.ltot += G.ltot & 1;
     for (int c = 0; c < 3; ++c) {
         G.own_off[c] = c * segA + kdz; G.own_len[c] = (long long)G.nzl * kdz;
@@ -1037,6 +1219,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     for (int c = 0; c < 4; ++c) even = even && (G.own_off[c] % 2 == 0) && (G.own_len[c] % 2 == 0);
     s.vec = even ? 2 : 1;
     s.nblkVec = vec_blocks(G.n_own, s.vec);
+    { int rc = solver_setup_ring(s); if (rc) return rc; }
     // ---- stencil launch shape ----
     {
         const int tx = (sdx + 31) / 32, ty = (sdy + 7) / 8;
@@ -1050,11 +1233,11 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         h->nblkAir = tx * ty * (int)h->airGrid.z;
         h->nblkCond = (h->ncond + 255) / 256;
     }
-    s.pstride = std::max(h->nblkAir + h->nblkCond, s.nblkVec) + 8;
-    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 4 * sizeof(double)));
+    s.pstride = std::max(std::max(h->nblkAir + h->nblkCond, s.nblkVec), 2 * 148) + 8;
+    CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 6 * sizeof(double)));
     s.multi = h->nranks > 1;
     s.spmv = [h](int mode, const VecSet &vs, const IterCtl &ctl) { return h_spmv(h, mode, vs, ctl); };
-    s.halo = [h](double *v, int check_done) { return h_halo(h, v, check_done); };
+    s.halo = [h](double *v, double *v2, int check_done) { return h_halo(h, v, v2, check_done); };
     s.allreduce = [h](int slot, int count) { return h_allreduce(h, slot, count); };
 
     // ---- validate conductor geometry, classify boundary-cell flags ----
@@ -1079,8 +1262,10 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     {
         const char *ef = getenv("EC3D_TMA");
         h->tma = (sdx % 2 == 0) && !(ef && atoi(ef) == 0);
-        const char *en = getenv("EC3D_NSTAGE");
-        h->nstage = (en && (atoi(en) == 3 || atoi(en) == 4 || atoi(en) == 5)) ? atoi(en) : 0;
+        const char *ec = getenv("EC3D_CCPS");
+        h->ccps = (ec && atoi(ec) == 1) ? 1 : 2;
+        const char *efu = getenv("EC3D_FUSE_S");
+        s.fused_sas = h->tma && !(efu && atoi(efu) == 0);
     }
     if (h->tma) {
         h->clsx = (sdx + 15) & ~15;
@@ -1105,17 +1290,23 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         }
         plan_spmv_items(G, zc, plane_major, items);
         h->zc = zc;
-        if (getenv("EC3D_VERBOSE")) fprintf(stderr, "ec3d: TMA SpMV work list: zc = %d, %zu items\n", zc, items.size());
-        std::vector<WorkItem> &heavy = items;
-        CUDA_TRY(cudaMalloc(&h->d_items, heavy.size() * sizeof(WorkItem)));
-        CUDA_TRY(cudaMemcpy(h->d_items, heavy.data(), heavy.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
-        h->airGrid = dim3((unsigned)heavy.size());
-        h->nblkAir = (int)heavy.size();
+        // two launches per SpMV: items with conductor cells, then lean items (each list keeps the planned order)
+        std::stable_partition(items.begin(), items.end(), [](const WorkItem &w) { return w.has_u != 0; });
+        h->nitems_cond = (int)std::count_if(items.begin(), items.end(), [](const WorkItem &w) { return w.has_u != 0; });
+        h->nitems_lean = (int)items.size() - h->nitems_cond;
+        if (getenv("EC3D_VERBOSE"))
+            fprintf(stderr, "ec3d: TMA SpMV work list: zc = %d, %d conductor + %d lean items, %d CTA/SM for conductor items, "
+                            "s-update %s, BLAS-1 %s\n", zc, h->nitems_cond, h->nitems_lean, h->ccps,
+                    s.fused_sas ? "fused into A*s" : "separate", s.ring ? "TMA ring" : "grid-stride");
+        CUDA_TRY(cudaMalloc(&h->d_items, items.size() * sizeof(WorkItem)));
+        CUDA_TRY(cudaMemcpy(h->d_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+        h->airGrid = dim3((unsigned)items.size());
+        h->nblkAir = (int)items.size();
         h->nblkCond = 0;
         if (h->nblkAir + 8 > s.pstride) {
             cudaFree(s.partials);
             s.pstride = h->nblkAir + 8;
-            CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 4 * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&s.partials, (size_t)s.pstride * 6 * sizeof(double)));
         }
     }
     // ---- sources ----
@@ -1319,7 +1510,7 @@ extern "C" int ec3d_apply_operator(ec3d_handle *h, const double *x, double *y)
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = copy_in(h, h->tmpx, x);
     if (rc) return rc;
-    VecSet vs{h->tmpx, h->tmpy, nullptr, nullptr, nullptr, nullptr, nullptr};
+    VecSet vs{h->tmpx, h->tmpy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const IterCtl ctl{h->sol.sc, h->sol.iter_base, 0};
     h->launches += h_spmv(h, MODE_PLAIN, vs, ctl);
     if ((rc = copy_out(h, y, h->tmpy))) return rc;
@@ -1387,7 +1578,7 @@ static int stage_scatter(ec3d_handle *h, const double *fun_vely, const double *v
 static int stage_rhs_pre(ec3d_handle *h)
 {
     if (h->size_PHYS_C == 0) return EC3D_OK;
-    int rc = h_halo(h, h->Uaf);      // the U-row right-hand side reads Az(k+-1) of Uaf
+    int rc = h_halo(h, h->Uaf, nullptr, 0);      // the U-row right-hand side reads Az(k+-1) of Uaf
     if (rc) return rc;
     h->sol.x_halo_fresh = (h->sol.X == h->Uaf);   // the solve's initial residual reuses it
     if (h->ncond) {
@@ -1615,24 +1806,33 @@ extern "C" int ec3d_bench_kernel(ec3d_handle *h, int32_t which, int32_t warm, in
     CUDA_TRY(cudaSetDevice(h->device));
     Solver &s = h->sol;
     const SlabGeom &G = h->G;
-    const unsigned nb = (unsigned)s.nblkVec;
     const IterCtl ctl{s.sc, s.iter_base, 1};
+    if (which == 5 && s.multi) { ec3d_set_error("whole-iteration timing is single-rank only"); return EC3D_ERR_UNSUPPORTED; }
     auto one = [&]() -> int {
         switch (which) {
-        case 0: { VecSet vs{s.P, s.AP, s.R0, nullptr, nullptr, nullptr, nullptr}; h->launches += h_spmv(h, MODE_AP, vs, ctl); break; }
-        case 1: { VecSet vs{s.S, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr}; h->launches += h_spmv(h, MODE_AS, vs, ctl); break; }
-        case 2:
-            if (s.vec == 2) k_s_update<2><<<nb, 256, 0, h->st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
-            else k_s_update<1><<<nb, 256, 0, h->st>>>(G, s.R, s.AP, s.S, ctl, s.partials, s.pstride, nb);
-            LAUNCHED(h->launches); break;
-        case 3:
-            if (s.vec == 2) k_xr_update<2><<<nb, 256, 0, h->st>>>(G, h->tmpx, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
-            else k_xr_update<1><<<nb, 256, 0, h->st>>>(G, h->tmpx, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
-            LAUNCHED(h->launches); break;
-        case 4:
-            if (s.vec == 2) k_p_update<2><<<nb, 256, 0, h->st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
-            else k_p_update<1><<<nb, 256, 0, h->st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
-            LAUNCHED(h->launches); break;
+        case 0: h->launches += h_spmv(h, MODE_AP, vecset_ap(s), ctl); break;
+        case 1:
+            if (s.fused_sas) h->launches += h_spmv(h, MODE_SAS, vecset_sas(s), ctl);
+            else h->launches += h_spmv(h, MODE_AS, vecset_as(s), ctl);
+            break;
+        case 2: { const long long l0 = s.launches; launch_s_update(s, ctl); h->launches += s.launches - l0; s.launches = l0; break; }
+        case 3: {
+            double *saveX = s.X;
+            const long long l0 = s.launches;
+            launch_xr_update(s, h->tmpx, ctl);
+            h->launches += s.launches - l0; s.launches = l0; s.X = saveX;
+            break;
+        }
+        case 4: { const long long l0 = s.launches; launch_p_update(s, ctl); h->launches += s.launches - l0; s.launches = l0; break; }
+        case 5: {                                            // one whole iteration (no exit: tol = 0)
+            double *saveX = s.X;
+            const long long l0 = s.launches;
+            s.X = h->tmpx;
+            const int rc = solver_enqueue_iteration(s, 1);
+            h->launches += s.launches - l0; s.launches = l0; s.X = saveX;
+            if (rc) return rc;
+            break;
+        }
         default: return EC3D_ERR_ARG;
         }
         return EC3D_OK;

@@ -13,6 +13,7 @@
 // and fields -- are reproducible run to run AND identical for 1, 2, 4, 8 GPUs; they differ from the
 // reference's sequential dot_product only by the reference's own rounding error.
 #pragma once
+#include "ec3d_async.cuh"
 #include "ec3d_common.cuh"
 #include "ec3d_rows.cuh"
 
@@ -20,14 +21,18 @@
 #define DADD(a, b) __dadd_rn((a), (b))
 #define DSUB(a, b) __dsub_rn((a), (b))
 
-enum { MODE_PLAIN = 0, MODE_AP = 1, MODE_AS = 2, MODE_INIT = 3 };
+// MODE_SAS (TMA SpMV only): the input is s = r - alpha*Ap formed on the fly from x = r and x2 = Ap
+// (solvers.f90:33 fused into the A*s of :39); the kernel also stores s and reduces ||s||^2.
+enum { MODE_PLAIN = 0, MODE_AP = 1, MODE_AS = 2, MODE_INIT = 3, MODE_SAS = 4 };
 
 struct VecSet {
-    const double *x;   // SpMV input
+    const double *x;   // SpMV input (MODE_SAS: r)
     double *y;         // SpMV output (AP / AS / plain)
     const double *r0;  // MODE_AP
     const double *b;   // MODE_INIT
     double *R, *R0, *P;// MODE_INIT outputs
+    const double *x2;  // MODE_SAS: Ap
+    double *S;         // MODE_SAS: s output
 };
 
 // --------------------------------------------------------------------------------------------
@@ -86,42 +91,48 @@ __device__ __forceinline__ dd block_sum(dd v, double *sh /* >= 64 doubles */)
 
 // Stores this block's partial(s); the last block of the GROUP of kernels that share `sc->counter`
 // (expected = total number of blocks that will call this with the same partials array) sums all
-// partials and writes sc->red[slot0], sc->red[slot1] (rounded; with several ranks the unrounded
-// double-double goes to red / red_lo and the cross-rank exchange rounds after summing the ranks).
-// partials: 4 * pstride doubles.
+// partials and writes sc->red[slot0..2] (rounded; with several ranks the unrounded double-double
+// goes to red / red_lo and the cross-rank exchange rounds after summing the ranks).
+// partials: 2 * NRED * pstride doubles.
 template <int NRED>
-__device__ __forceinline__ void reduce_epilogue(dd a0, dd a1, double *partials, int pstride, int pidx,
-                                                unsigned expected, Scal *sc, int slot0, int slot1, double *sh)
+__device__ __forceinline__ void reduce_epilogue(dd a0, dd a1, dd a2, double *partials, int pstride, int pidx,
+                                                unsigned expected, Scal *sc, int slot0, int slot1, int slot2, double *sh)
 {
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     const int nthr = blockDim.x * blockDim.y * blockDim.z;
     dd s0 = block_sum(a0, sh);
-    dd s1 = dd_zero();
+    dd s1 = dd_zero(), s2 = dd_zero();
     if (NRED > 1) s1 = block_sum(a1, sh);
+    if (NRED > 2) s2 = block_sum(a2, sh);
     __shared__ unsigned ticket_s;
     if (tid == 0) {
         partials[2 * pidx] = s0.hi; partials[2 * pidx + 1] = s0.lo;
         if (NRED > 1) { partials[2 * (pstride + pidx)] = s1.hi; partials[2 * (pstride + pidx) + 1] = s1.lo; }
+        if (NRED > 2) { partials[2 * (2 * pstride + pidx)] = s2.hi; partials[2 * (2 * pstride + pidx) + 1] = s2.lo; }
         __threadfence();
         ticket_s = atomicAdd(&sc->counter, 1u);
     }
     __syncthreads();
     if (ticket_s != expected - 1) return;
     __threadfence();
-    dd t0 = dd_zero(), t1 = dd_zero();
+    dd t0 = dd_zero(), t1 = dd_zero(), t2 = dd_zero();
     for (unsigned q = tid; q < expected; q += nthr) {
         dd_add_dd(t0, dd{__ldcg(partials + 2 * q), __ldcg(partials + 2 * q + 1)});
         if (NRED > 1) dd_add_dd(t1, dd{__ldcg(partials + 2 * (pstride + q)), __ldcg(partials + 2 * (pstride + q) + 1)});
+        if (NRED > 2) dd_add_dd(t2, dd{__ldcg(partials + 2 * (2 * pstride + q)), __ldcg(partials + 2 * (2 * pstride + q) + 1)});
     }
     t0 = block_sum(t0, sh);
     if (NRED > 1) t1 = block_sum(t1, sh);
+    if (NRED > 2) t2 = block_sum(t2, sh);
     if (tid == 0) {
         if (sc->multi) {
             sc->red[slot0] = t0.hi; sc->red_lo[slot0] = t0.lo;
             if (NRED > 1) { sc->red[slot1] = t1.hi; sc->red_lo[slot1] = t1.lo; }
+            if (NRED > 2) { sc->red[slot2] = t2.hi; sc->red_lo[slot2] = t2.lo; }
         } else {
             sc->red[slot0] = dd_round(t0);
             if (NRED > 1) sc->red[slot1] = dd_round(t1);
+            if (NRED > 2) sc->red[slot2] = dd_round(t2);
         }
         sc->counter = 0u;
         __threadfence();
@@ -198,6 +209,7 @@ __device__ __forceinline__ bool spmv_guard(const IterCtl &c)
         if (c.sc->done) return false;
         if (s_converged(c.sc)) return false;
     }
+    if (MODE == MODE_SAS) return !c.sc->done;      // ||s|| is only known after this kernel: A*s is speculative
     return true;
 }
 
@@ -267,55 +279,22 @@ k_air_spmv(const SlabGeom G, const Coef cf, const int *__restrict__ geo, const V
         const int pidx = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         // INIT reduces (bb, rr), AS reduces (ass, asas), AP reduces (apr0)
         if (MODE == MODE_AP)
-            reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
-                               RED_APR0, RED_APR0, sh);
+            reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), dd_zero(), partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
+                               RED_APR0, RED_APR0, RED_APR0, sh);
         else if (MODE == MODE_AS)
-            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
-                               RED_ASS, RED_ASAS, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, dd_zero(), partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
+                               RED_ASS, RED_ASAS, RED_ASAS, sh);
         else
-            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
-                               RED_BB, RED_RR_INIT, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, dd_zero(), partials, pstride, pidx, finalize_here ? expected : 0xffffffffu, ctl.sc,
+                               RED_BB, RED_RR_INIT, RED_RR_INIT, sh);
     }
 }
 
 // --------------------------------------------------------------------------------------------
-// 16-byte helpers and the pair epilogue shared by the SpMV kernels that own two x-adjacent cells
-// per thread (ec3d_tma.cuh).
+// 16-byte helpers of the kernels that own two adjacent entries per thread.
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
-
-// Stores / accumulates the rows ya, yb of the cells at idx, idx+1 (wa / wb: row exists).  aux is
-// r0 (MODE_AP) or b (MODE_INIT) at idx; xa, xb the SpMV input at idx (MODE_AS).  Same arithmetic
-// and accumulation order as row_epilogue for cell a, then cell b.
-template <int MODE>
-__device__ __forceinline__ void pair_epilogue_pre(double ya, double yb, bool wa, bool wb, long long idx, double xa,
-                                                  double xb, double2 aux, const VecSet &vs, double &a0, double &a1)
-{
-    if (MODE == MODE_INIT) {
-        const double ra = DSUB(aux.x, ya), rb = DSUB(aux.y, yb);
-        if (wa && wb) { st2(vs.R + idx, ra, rb); st2(vs.R0 + idx, ra, rb); st2(vs.P + idx, ra, rb); }
-        else {
-            if (wa) { vs.R[idx] = ra; vs.R0[idx] = ra; vs.P[idx] = ra; }
-            if (wb) { vs.R[idx + 1] = rb; vs.R0[idx + 1] = rb; vs.P[idx + 1] = rb; }
-        }
-        if (wa) { a0 = DADD(a0, DMUL(aux.x, aux.x)); a1 = DADD(a1, DMUL(ra, ra)); }
-        if (wb) { a0 = DADD(a0, DMUL(aux.y, aux.y)); a1 = DADD(a1, DMUL(rb, rb)); }
-        return;
-    }
-    if (wa && wb) st2(vs.y + idx, ya, yb);
-    else {
-        if (wa) vs.y[idx] = ya;
-        if (wb) vs.y[idx + 1] = yb;
-    }
-    if (MODE == MODE_AP) {
-        if (wa) a0 = DADD(a0, DMUL(ya, aux.x));
-        if (wb) a0 = DADD(a0, DMUL(yb, aux.y));
-    } else if (MODE == MODE_AS) {
-        if (wa) { a0 = DADD(a0, DMUL(ya, xa)); a1 = DADD(a1, DMUL(ya, ya)); }
-        if (wb) { a0 = DADD(a0, DMUL(yb, xb)); a1 = DADD(a1, DMUL(yb, yb)); }
-    }
-}
 
 // --------------------------------------------------------------------------------------------
 // K2b: matrix-free SpMV, conductor cells: three A rows with convection, 2C/dt and grad-U coupling
@@ -366,11 +345,11 @@ k_cond_spmv(const SlabGeom G, const Coef cf, const MatCoef *__restrict__ mcs, co
     if (MODE != MODE_PLAIN) {
         const int pidx = pbase + blockIdx.x;
         if (MODE == MODE_AP)
-            reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_APR0, RED_APR0, sh);
+            reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_APR0, RED_APR0, RED_APR0, sh);
         else if (MODE == MODE_AS)
-            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, RED_ASAS, sh);
         else
-            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, pidx, expected, ctl.sc, RED_BB, RED_RR_INIT, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_BB, RED_RR_INIT, RED_RR_INIT, sh);
     }
 }
 
@@ -411,11 +390,11 @@ k_csr_spmv(const int n, const int *__restrict__ irow, const int *__restrict__ jc
     if (r < n) row_epilogue<MODE>(s, r, vs.x[r], vs, a0, a1);
     if (MODE != MODE_PLAIN) {
         if (MODE == MODE_AP)
-            reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), partials, pstride, blockIdx.x, expected, ctl.sc, RED_APR0, RED_APR0, sh);
+            reduce_epilogue<1>(dd{a0, 0.0}, dd_zero(), dd_zero(), partials, pstride, blockIdx.x, expected, ctl.sc, RED_APR0, RED_APR0, RED_APR0, sh);
         else if (MODE == MODE_AS)
-            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, blockIdx.x, expected, ctl.sc, RED_ASS, RED_ASAS, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, dd_zero(), partials, pstride, blockIdx.x, expected, ctl.sc, RED_ASS, RED_ASAS, RED_ASAS, sh);
         else
-            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, partials, pstride, blockIdx.x, expected, ctl.sc, RED_BB, RED_RR_INIT, sh);
+            reduce_epilogue<2>(dd{a0, 0.0}, dd{a1, 0.0}, dd_zero(), partials, pstride, blockIdx.x, expected, ctl.sc, RED_BB, RED_RR_INIT, RED_RR_INIT, sh);
     }
 }
 
@@ -475,7 +454,7 @@ k_s_update(const SlabGeom G, const double *__restrict__ R, const double *__restr
             dd_add_d(acc, DMUL(s, s));
         }
     }
-    reduce_epilogue<1>(acc, dd_zero(), partials, pstride, blockIdx.x, expected, sc, RED_SS, RED_SS, sh);
+    reduce_epilogue<1>(acc, dd_zero(), dd_zero(), partials, pstride, blockIdx.x, expected, sc, RED_SS, RED_SS, RED_SS, sh);
 }
 
 // K5: if ||S|| converged: X = X + alpha*P (solvers.f90:36).  Else omega = (AS,S)/(AS,AS);
@@ -530,7 +509,7 @@ k_xr_update(const SlabGeom G, double *__restrict__ X, const double *__restrict__
             dd_add_d(a1, DMUL(r, R0[l]));
         }
     }
-    reduce_epilogue<2>(a0, a1, partials, pstride, blockIdx.x, expected, sc, RED_RR, RED_RR0N, sh);
+    reduce_epilogue<2>(a0, a1, dd_zero(), partials, pstride, blockIdx.x, expected, sc, RED_RR, RED_RR0N, RED_RR0N, sh);
 }
 
 // K6: exit tests, beta, P = R + beta*(P - omega*AP), restart.     solvers.f90:34-49
@@ -591,6 +570,283 @@ k_p_update(const SlabGeom G, double *__restrict__ P, const double *__restrict__ 
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// TMA-ring BLAS-1 kernels (main path).  The grid-stride kernels above keep one 16-byte load per
+// stream and thread in flight and, on 3.4 GB vectors whose bases differ by multiples of 0.5 MiB,
+// collide in the L2-slice / DRAM-channel hash: 0.78-0.83 of the copy peak on plate(512) with DRAM
+// reads 15-21 % above the algorithmic bytes (profiles/r02_ncu_blas1_plate512_r01kernels.txt).
+// Here a persistent CTA per SM streams chunks of CH doubles of every input vector into a ring of
+// shared-memory stages with linear bulk copies (cp.async.bulk, completed on an mbarrier); the
+// copy engine keeps (NST-1) x NIN x 8 KB in flight per SM regardless of registers, and the same
+// arithmetic runs out of shared memory.  Measured in isolation (scripts/stream_probe.cu): 1.00-1.05
+// of the measured copy peak at 0.4 GB and 3.4 GB per vector, any vector spacing.
+// Chunks never straddle the four owned segments of the local layout; chunk c is processed by CTA
+// c % gridDim.x so that concurrently running CTAs stream neighbouring addresses.  The dot products
+// keep the pair grouping of the grid-stride kernels (entries 2u, 2u+1 of the owned numbering, one
+// fma; everything above in double-double), i.e. the same rounded results.
+// --------------------------------------------------------------------------------------------
+constexpr int V1_CH = 1024;                      // doubles per chunk and stream (8 KB)
+
+struct ChunkMap {                                // chunks of the four owned segments
+    long long cum[5];
+    __device__ __forceinline__ void init(const SlabGeom &G)
+    {
+        cum[0] = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) cum[s + 1] = cum[s] + (G.own_len[s] + V1_CH - 1) / V1_CH;
+    }
+    // local offset and length (doubles, even) of chunk c
+    __device__ __forceinline__ void locate(const SlabGeom &G, long long c, long long &loc, int &len) const
+    {
+        const int s = (int)(c >= cum[1]) + (int)(c >= cum[2]) + (int)(c >= cum[3]);
+        const long long first = (s == 0) ? 0 : (s == 1) ? cum[1] : (s == 2) ? cum[2] : cum[3];   // (no dynamic indexing: registers)
+        const long long o = (c - first) * V1_CH;
+        loc = G.own_off[s] + o;
+        len = (int)min((long long)V1_CH, G.own_len[s] - o);
+    }
+};
+
+template <int NIN, int NST>
+struct BulkRing {
+    static constexpr int STAGE_BYTES = NIN * V1_CH * 8;
+    unsigned char *smem;
+    unsigned long long *full, *empty;
+    const double *in[NIN];
+    ChunkMap cm;
+    long long c0, cs, mine;
+
+    __device__ __forceinline__ void issue(const SlabGeom &G, long long i)
+    {
+        const int s = (int)(i % NST);
+        long long loc; int len;
+        cm.locate(G, c0 + i * cs, loc, len);
+        unsigned char *st = smem + s * STAGE_BYTES;
+        tma::mbar_expect_tx(full + s, (uint32_t)(NIN * len * 8));
+#pragma unroll
+        for (int v = 0; v < NIN; ++v) tma::bulk_load(st + v * V1_CH * 8, in[v] + loc, (uint32_t)(len * 8), full + s);
+    }
+    __device__ __forceinline__ void start(const SlabGeom &G, unsigned char *smem_, unsigned long long *full_,
+                                          unsigned long long *empty_)
+    {
+        smem = smem_; full = full_; empty = empty_;
+        cm.init(G);
+        c0 = blockIdx.x; cs = gridDim.x;
+        const long long nch = cm.cum[4];
+        mine = (nch > c0) ? (nch - c0 + cs - 1) / cs : 0;
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < NST; ++s) { tma::mbar_init(full + s, 1); tma::mbar_init(empty + s, blockDim.x / 32); }
+            tma::fence_barrier_init();
+            tma::fence_proxy_async();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (long long i = 0; i < min((long long)NST, mine); ++i) issue(G, i);
+    }
+    // wait for chunk i; returns its stage
+    __device__ __forceinline__ const double *acquire(long long i) const
+    {
+        tma::mbar_wait(full + (int)(i % NST), (uint32_t)((i / NST) & 1));
+        return reinterpret_cast<const double *>(smem + (int)(i % NST) * STAGE_BYTES);
+    }
+    // every warp calls this once it has read chunk i into registers; thread 0 re-arms the stage
+    // (consumer arrive + producer wait on the `empty` barrier order the generic-proxy reads before
+    // the async-proxy refill)
+    __device__ __forceinline__ void release(const SlabGeom &G, long long i)
+    {
+        const int s = (int)(i % NST);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) tma::mbar_arrive(empty + s);
+        if (threadIdx.x == 0 && i + NST < mine) {
+            tma::mbar_wait(empty + s, (uint32_t)((i / NST) & 1));
+            issue(G, i + NST);
+        }
+    }
+};
+
+constexpr int XR_NST = 3, P_NST = 4, S_NST = 4;
+constexpr int v1_smem_bytes(int nin, int nst) { return nin * V1_CH * 8 * nst + 128; }
+
+__device__ __forceinline__ unsigned char *align128(unsigned char *p)
+{
+    return p + ((128u - (tma::smem_u32(p) & 127u)) & 127u);
+}
+
+// K5 (TMA ring): X = X + alpha*P [+ omega*S]; R = S - omega*AS; ||R||^2, (R,R0).   solvers.f90:34-44
+__global__ void __launch_bounds__(256, 1)
+k_xr_update_tma(const SlabGeom G, double *__restrict__ X, const double *__restrict__ P, const double *__restrict__ S,
+                const double *__restrict__ AS, double *__restrict__ R, const double *__restrict__ R0, const IterCtl ctl,
+                double *partials, const int pstride, const unsigned expected)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ double sh[64];
+    __shared__ __align__(8) unsigned long long full[XR_NST], empty[XR_NST];
+    Scal *sc = ctl.sc;
+    if (sc->done) return;
+    const double alpha = sc->alpha;
+    const int tid = threadIdx.x;
+    if (s_converged(sc)) {                                  // exit of solvers.f90:34-38: X = X + alpha*P only
+        ChunkMap cm; cm.init(G);
+        for (long long c = blockIdx.x; c < cm.cum[4]; c += gridDim.x) {
+            long long loc; int len;
+            cm.locate(G, c, loc, len);
+            for (int e = 2 * tid; e < len; e += 512) {
+                double2 x = ld2(X + loc + e);
+                const double2 p = ld2(P + loc + e);
+                st2(X + loc + e, DADD(x.x, DMUL(alpha, p.x)), DADD(x.y, DMUL(alpha, p.y)));
+            }
+        }
+        return;
+    }
+    const double omega = sc->red[RED_ASS] / sc->red[RED_ASAS];
+    if (is_block0()) sc->omega = omega;
+    BulkRing<5, XR_NST> ring;
+    ring.in[0] = X; ring.in[1] = P; ring.in[2] = S; ring.in[3] = AS; ring.in[4] = R0;
+    ring.start(G, align128(smem_raw), full, empty);
+    dd a0 = dd_zero(), a1 = dd_zero();
+    for (long long i = 0; i < ring.mine; ++i) {
+        const double *st = ring.acquire(i);
+        long long loc; int len;
+        ring.cm.locate(G, ring.c0 + i * ring.cs, loc, len);
+        double2 x[2], p[2], s[2], as[2], r0[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = 2 * (tid + u * 256);
+            if (e < len) {
+                x[u] = ld2(st + e); p[u] = ld2(st + V1_CH + e); s[u] = ld2(st + 2 * V1_CH + e);
+                as[u] = ld2(st + 3 * V1_CH + e); r0[u] = ld2(st + 4 * V1_CH + e);
+            }
+        }
+        ring.release(G, i);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = 2 * (tid + u * 256);
+            if (e < len) {
+                double2 r;
+                x[u].x = DADD(DADD(x[u].x, DMUL(alpha, p[u].x)), DMUL(omega, s[u].x));
+                x[u].y = DADD(DADD(x[u].y, DMUL(alpha, p[u].y)), DMUL(omega, s[u].y));
+                r.x = DSUB(s[u].x, DMUL(omega, as[u].x));
+                r.y = DSUB(s[u].y, DMUL(omega, as[u].y));
+                st2(X + loc + e, x[u].x, x[u].y);
+                st2(R + loc + e, r.x, r.y);
+                dd_add_d(a0, __fma_rn(r.y, r.y, DMUL(r.x, r.x)));
+                dd_add_d(a1, __fma_rn(r.y, r0[u].y, DMUL(r.x, r0[u].x)));
+            }
+        }
+    }
+    reduce_epilogue<2>(a0, a1, dd_zero(), partials, pstride, blockIdx.x, expected, sc, RED_RR, RED_RR0N, RED_RR0N, sh);
+}
+
+// K6 (TMA ring): exit tests, beta, P = R + beta*(P - omega*AP), restart.     solvers.f90:34-49
+__global__ void __launch_bounds__(256, 2)
+k_p_update_tma(const SlabGeom G, double *__restrict__ P, const double *__restrict__ R, const double *__restrict__ AP,
+               double *__restrict__ R0, const IterCtl ctl)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full[P_NST], empty[P_NST];
+    Scal *sc = ctl.sc;
+    if (sc->done) return;
+    const int it = *ctl.iter_base + ctl.it_off;
+    const double bnorm = sqrt(sc->red[RED_BB]);
+    if (s_converged(sc)) {                                              // exit taken at solvers.f90:34-38
+        if (is_block0()) { sc->exit_kind = 1; sc->final_iter = it; sc->done = 1; }
+        return;
+    }
+    if (sqrt(sc->red[RED_RR]) / bnorm < sc->tol) {                      // solvers.f90:43
+        if (is_block0()) { sc->exit_kind = 2; sc->final_iter = it; sc->done = 1; }
+        return;
+    }
+    const double rr0 = (it == 1) ? sc->red[RED_RR_INIT] : sc->rr0[it & 1];
+    const double rr0n = sc->red[RED_RR0N];
+    const double alpha = sc->alpha, omega = sc->omega;
+    const double beta = (alpha / omega) * rr0n / rr0;                   // solvers.f90:45
+    const bool restart = fabs(rr0n) / bnorm < sc->tol;                  // solvers.f90:47
+    if (is_block0()) {
+        sc->beta = beta;
+        sc->rr0[(it + 1) & 1] = restart ? sc->red[RED_RR] : rr0n;      // next (R,R0), solvers.f90:31
+        if (restart) sc->restarts += 1;
+    }
+    const int tid = threadIdx.x;
+    if (restart) {                                                      // R0 = R; P = R   (rare: plain loads)
+        ChunkMap cm; cm.init(G);
+        for (long long c = blockIdx.x; c < cm.cum[4]; c += gridDim.x) {
+            long long loc; int len;
+            cm.locate(G, c, loc, len);
+            for (int e = 2 * tid; e < len; e += 512) {
+                const double2 r = ld2(R + loc + e);
+                st2(R0 + loc + e, r.x, r.y);
+                st2(P + loc + e, r.x, r.y);
+            }
+        }
+        return;
+    }
+    BulkRing<3, P_NST> ring;
+    ring.in[0] = R; ring.in[1] = P; ring.in[2] = AP;
+    ring.start(G, align128(smem_raw), full, empty);
+    for (long long i = 0; i < ring.mine; ++i) {
+        const double *st = ring.acquire(i);
+        long long loc; int len;
+        ring.cm.locate(G, ring.c0 + i * ring.cs, loc, len);
+        double2 r[2], p[2], ap[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = 2 * (tid + u * 256);
+            if (e < len) { r[u] = ld2(st + e); p[u] = ld2(st + V1_CH + e); ap[u] = ld2(st + 2 * V1_CH + e); }
+        }
+        ring.release(G, i);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = 2 * (tid + u * 256);
+            if (e < len)
+                st2(P + loc + e, DADD(r[u].x, DMUL(beta, DSUB(p[u].x, DMUL(omega, ap[u].x)))),
+                    DADD(r[u].y, DMUL(beta, DSUB(p[u].y, DMUL(omega, ap[u].y)))));
+        }
+    }
+}
+
+// K3 (TMA ring; CSR drop-in path, where the SpMV is not the fused MODE_SAS kernel):
+// alpha = rr0/(AP,R0); S = R - alpha*AP; ||S||^2.            solvers.f90:31-34
+__global__ void __launch_bounds__(256, 2)
+k_s_update_tma(const SlabGeom G, const double *__restrict__ R, const double *__restrict__ AP, double *__restrict__ S,
+               const IterCtl ctl, double *partials, const int pstride, const unsigned expected)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ double sh[64];
+    __shared__ __align__(8) unsigned long long full[S_NST], empty[S_NST];
+    Scal *sc = ctl.sc;
+    if (sc->done) return;
+    const int it = *ctl.iter_base + ctl.it_off;
+    const double rr0 = (it == 1) ? sc->red[RED_RR_INIT] : sc->rr0[it & 1];
+    const double alpha = rr0 / sc->red[RED_APR0];
+    if (is_block0()) sc->alpha = alpha;
+    const int tid = threadIdx.x;
+    BulkRing<2, S_NST> ring;
+    ring.in[0] = R; ring.in[1] = AP;
+    ring.start(G, align128(smem_raw), full, empty);
+    dd acc = dd_zero();
+    for (long long i = 0; i < ring.mine; ++i) {
+        const double *st = ring.acquire(i);
+        long long loc; int len;
+        ring.cm.locate(G, ring.c0 + i * ring.cs, loc, len);
+        double2 r[2], ap[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = 2 * (tid + u * 256);
+            if (e < len) { r[u] = ld2(st + e); ap[u] = ld2(st + V1_CH + e); }
+        }
+        ring.release(G, i);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = 2 * (tid + u * 256);
+            if (e < len) {
+                const double sx = DSUB(r[u].x, DMUL(alpha, ap[u].x)), sy = DSUB(r[u].y, DMUL(alpha, ap[u].y));
+                st2(S + loc + e, sx, sy);
+                dd_add_d(acc, __fma_rn(sy, sy, DMUL(sx, sx)));
+            }
+        }
+    }
+    reduce_epilogue<1>(acc, dd_zero(), dd_zero(), partials, pstride, blockIdx.x, expected, sc, RED_SS, RED_SS, RED_SS, sh);
+}
+
 __global__ void k_solver_reset(Scal *sc, int *iter_base, double tol, int itmax, int multi)
 {
     for (int q = 0; q < 8; ++q) { sc->red[q] = 0.0; sc->red_lo[q] = 0.0; }
@@ -604,21 +860,22 @@ __global__ void k_solver_reset(Scal *sc, int *iter_base, double tol, int itmax, 
 
 __global__ void k_iter_advance(int *iter_base, int by) { *iter_base += by; }
 
-// NCCL path of the cross-rank reduction: (hi, lo) of up to two results <-> gather buffer
-__global__ void k_red_pack(const Scal *sc, int slot, int count, double *mine /* 4 doubles */)
+// NCCL path of the cross-rank reduction: (hi, lo) of up to three results <-> gather buffer
+#define RED_W 6     // doubles exchanged per rank and reduction point: up to 3 results x (hi, lo)
+__global__ void k_red_pack(const Scal *sc, int slot, int count, double *mine /* RED_W doubles */)
 {
     if (threadIdx.x != 0) return;
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < RED_W / 2; ++q) {
         mine[2 * q] = q < count ? sc->red[slot + q] : 0.0;
         mine[2 * q + 1] = q < count ? sc->red_lo[slot + q] : 0.0;
     }
 }
-__global__ void k_red_unpack(Scal *sc, int slot, int count, const double *all /* [nranks][4] */, int nranks)
+__global__ void k_red_unpack(Scal *sc, int slot, int count, const double *all /* [nranks][RED_W] */, int nranks)
 {
     if (threadIdx.x != 0) return;
     for (int q = 0; q < count; ++q) {
         dd t = dd_zero();
-        for (int r = 0; r < nranks; ++r) dd_add_dd(t, dd{all[4 * r + 2 * q], all[4 * r + 2 * q + 1]});
+        for (int r = 0; r < nranks; ++r) dd_add_dd(t, dd{all[RED_W * r + 2 * q], all[RED_W * r + 2 * q + 1]});
         sc->red[slot + q] = dd_round(t);
     }
 }

@@ -28,7 +28,7 @@
 struct CommBlock {                                   // written by peers
     unsigned long long halo_flag[2];                 // [0] from rank-1, [1] from rank+1: epoch of their last push
     unsigned long long red_flag[EC3D_MAX_RANKS];     // epoch of rank r's last contribution
-    double red_val[2][EC3D_MAX_RANKS][4];            // [epoch parity][rank][hi0, lo0, hi1, lo1]
+    double red_val[2][EC3D_MAX_RANKS][8];            // [epoch parity][rank][hi0, lo0, hi1, lo1, hi2, lo2, -, -]
 };
 
 struct CommLocal {                                   // this rank only
@@ -71,42 +71,43 @@ __device__ __forceinline__ bool wait_epoch(const unsigned long long *p, unsigned
     return true;
 }
 
-// Copies this rank's boundary planes of local vector `vidx` into the neighbours' halo slots.
-// Work units are 16-byte pairs; segment list (up to 8): 3 A planes + U planes towards each side.
+// Copies this rank's boundary planes of local vector `vidx` (and `vidx2` when >= 0) into the neighbours'
+// halo slots.  Work units are 16-byte pairs; per vector up to 8 segments: 3 A planes + U planes towards each side.
 __global__ void __launch_bounds__(256)
-k_halo_push(const SlabGeom G, const PeerTable pt, double *__restrict__ vecs, const int vidx, const long long nU_send_lo,
-            const long long nU_send_hi, const Scal *sc, const int check_done, CommLocal *cl)
+k_halo_push(const SlabGeom G, const PeerTable pt, double *__restrict__ vecs, const int vidx, const int vidx2,
+            const long long nU_send_lo, const long long nU_send_hi, const Scal *sc, const int check_done, CommLocal *cl)
 {
     if (check_done && sc->done) return;
-    const double *src = vecs + (long long)vidx * G.ltot;
     const long long kdz = G.kdz;
-    // towards rank-1: my first owned plane -> its upper halo plane; my first two U planes -> its U halo above
-    if (pt.vecs_lo) {
-        double *dst = pt.vecs_lo + (long long)vidx * pt.g_lo.ltot;
-        for (int c = 0; c < 3; ++c) {
-            const double2 *s2 = reinterpret_cast<const double2 *>(src + c * G.segA + kdz);
-            double2 *d2 = reinterpret_cast<double2 *>(dst + c * pt.g_lo.segA + (long long)(pt.g_lo.nzl + 1) * kdz);
-            for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < kdz / 2; q += (long long)gridDim.x * blockDim.x)
-                d2[q] = s2[q];
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, tstep = (long long)gridDim.x * blockDim.x;
+    for (int w = 0; w < 2; ++w) {
+        const int vi = w == 0 ? vidx : vidx2;
+        if (vi < 0) continue;
+        const double *src = vecs + (long long)vi * G.ltot;
+        // towards rank-1: my first owned plane -> its upper halo plane; my first two U planes -> its U halo above
+        if (pt.vecs_lo) {
+            double *dst = pt.vecs_lo + (long long)vi * pt.g_lo.ltot;
+            for (int c = 0; c < 3; ++c) {
+                const double2 *s2 = reinterpret_cast<const double2 *>(src + c * G.segA + kdz);
+                double2 *d2 = reinterpret_cast<double2 *>(dst + c * pt.g_lo.segA + (long long)(pt.g_lo.nzl + 1) * kdz);
+                for (long long q = t0; q < kdz / 2; q += tstep) d2[q] = s2[q];
+            }
+            const double *su = src + G.offU + G.nUlo;
+            double *du = dst + pt.g_lo.offU + pt.g_lo.nUlo + pt.g_lo.nUown;
+            for (long long q = t0; q < nU_send_lo; q += tstep) du[q] = su[q];
         }
-        const double *su = src + G.offU + G.nUlo;
-        double *du = dst + pt.g_lo.offU + pt.g_lo.nUlo + pt.g_lo.nUown;
-        for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nU_send_lo; q += (long long)gridDim.x * blockDim.x)
-            du[q] = su[q];
-    }
-    // towards rank+1: my last owned plane -> its lower halo plane; my last two U planes -> its U halo below
-    if (pt.vecs_hi) {
-        double *dst = pt.vecs_hi + (long long)vidx * pt.g_hi.ltot;
-        for (int c = 0; c < 3; ++c) {
-            const double2 *s2 = reinterpret_cast<const double2 *>(src + c * G.segA + (long long)G.nzl * kdz);
-            double2 *d2 = reinterpret_cast<double2 *>(dst + c * pt.g_hi.segA);
-            for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < kdz / 2; q += (long long)gridDim.x * blockDim.x)
-                d2[q] = s2[q];
+        // towards rank+1: my last owned plane -> its lower halo plane; my last two U planes -> its U halo below
+        if (pt.vecs_hi) {
+            double *dst = pt.vecs_hi + (long long)vi * pt.g_hi.ltot;
+            for (int c = 0; c < 3; ++c) {
+                const double2 *s2 = reinterpret_cast<const double2 *>(src + c * G.segA + (long long)G.nzl * kdz);
+                double2 *d2 = reinterpret_cast<double2 *>(dst + c * pt.g_hi.segA);
+                for (long long q = t0; q < kdz / 2; q += tstep) d2[q] = s2[q];
+            }
+            const double *su = src + G.offU + G.nUlo + G.nUown - nU_send_hi;
+            double *du = dst + pt.g_hi.offU;
+            for (long long q = t0; q < nU_send_hi; q += tstep) du[q] = su[q];
         }
-        const double *su = src + G.offU + G.nUlo + G.nUown - nU_send_hi;
-        double *du = dst + pt.g_hi.offU;
-        for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nU_send_hi; q += (long long)gridDim.x * blockDim.x)
-            du[q] = su[q];
     }
     // every block: make its stores visible system wide, then take a ticket; the last block signals
     __threadfence_system();
@@ -136,7 +137,7 @@ __global__ void k_halo_wait(const PeerTable pt, const Scal *sc, const int check_
     __threadfence_system();
 }
 
-// sc->red[slot .. slot+count) <- sum over ranks (count <= 2), in rank order on every rank
+// sc->red[slot .. slot+count) <- sum over ranks (count <= 3), in rank order on every rank
 __global__ void k_reduce_xchg(const PeerTable pt, Scal *sc, const int slot, const int count, const int force, CommLocal *cl)
 {
     if (!force && sc->done) return;              // count == 0, force != 0: a plain barrier over all ranks

@@ -43,72 +43,7 @@ constexpr int BW = TX + 4, BH = TY + 2;     // halo box: 2 extra columns each si
 constexpr int TILE_D = BW * BH;             // 680 doubles
 constexpr int TILE_BYTES = TILE_D * 8;      // 5440
 constexpr int XS_BYTES = 3 * TILE_BYTES;    // 16320: one TMA box 68 x 10 x 1 x 3
-constexpr int CLS_OFF = 16384;              // class-byte tile (64 x 8 bytes) inside a stage (128-byte aligned)
-constexpr int CLS_BYTES = TX * TY;          // 512
-constexpr int US_OFF = CLS_OFF + CLS_BYTES; // 16896 = 132 * 128: U tile
-constexpr int STAGE_BYTES = US_OFF + 5504;  // 22400 = 175 * 128
-constexpr int smem_bytes(int nstage) { return nstage * STAGE_BYTES + 128; }
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
-{
-    while (!mbar_try_wait(bar, parity)) {}
-}
-
-__device__ __forceinline__ void load4d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-
-__device__ __forceinline__ void load3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-// TMA prefetch of a tile into L2 (no shared-memory destination, no barrier)
-__device__ __forceinline__ void prefetch4d(const CUtensorMap *map, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-                 ::"l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void prefetch3d(const CUtensorMap *map, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-                 ::"l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
+constexpr int CLS_BYTES = TX * TY;          // 512: class-byte tile (64 x 8 bytes)
 
 // U values of one cell along one axis at offsets -2 .. +2
 struct U5 {
@@ -203,11 +138,12 @@ __global__ void k_build_cls2(const SlabGeom G, const int *__restrict__ geo, cons
 
 // Row epilogue of a cell pair: stores, and the fused BiCGSTABwr dot products.  The products of the
 // dots are accumulated with fma (the reference's sequential dot_product order is not reproducible
-// in parallel anyway; fewer roundings, half the FP64 instructions).
+// in parallel anyway; fewer roundings, half the FP64 instructions).  xa, xb = the SpMV input at the
+// two cells (MODE_SAS: s = r - alpha*Ap, which this kernel also materialises in vs.S).
 template <int MODE>
 __device__ __forceinline__ void pair_out(const double ya, const double yb, const bool wa, const bool wb, const long long idx,
                                          const double xa, const double xb, const double2 aux, const VecSet &vs,
-                                         double &a0, double &a1)
+                                         double &a0, double &a1, double &a2)
 {
     if (MODE == MODE_INIT) {
         const double ra = DSUB(aux.x, ya), rb = DSUB(aux.y, yb);
@@ -220,17 +156,19 @@ __device__ __forceinline__ void pair_out(const double ya, const double yb, const
         if (wb) { a0 = __fma_rn(aux.y, aux.y, a0); a1 = __fma_rn(rb, rb, a1); }
         return;
     }
-    if (wa && wb) st2(vs.y + idx, ya, yb);
-    else {
-        if (wa) vs.y[idx] = ya;
-        if (wb) vs.y[idx + 1] = yb;
+    if (wa && wb) {
+        st2(vs.y + idx, ya, yb);
+        if (MODE == MODE_SAS) st2(vs.S + idx, xa, xb);
+    } else {
+        if (wa) { vs.y[idx] = ya; if (MODE == MODE_SAS) vs.S[idx] = xa; }
+        if (wb) { vs.y[idx + 1] = yb; if (MODE == MODE_SAS) vs.S[idx + 1] = xb; }
     }
     if (MODE == MODE_AP) {
         if (wa) a0 = __fma_rn(ya, aux.x, a0);
         if (wb) a0 = __fma_rn(yb, aux.y, a0);
-    } else if (MODE == MODE_AS) {
-        if (wa) { a0 = __fma_rn(ya, xa, a0); a1 = __fma_rn(ya, ya, a1); }
-        if (wb) { a0 = __fma_rn(yb, xb, a0); a1 = __fma_rn(yb, yb, a1); }
+    } else if (MODE == MODE_AS || MODE == MODE_SAS) {
+        if (wa) { a0 = __fma_rn(ya, xa, a0); a1 = __fma_rn(ya, ya, a1); if (MODE == MODE_SAS) a2 = __fma_rn(xa, xa, a2); }
+        if (wb) { a0 = __fma_rn(yb, xb, a0); a1 = __fma_rn(yb, yb, a1); if (MODE == MODE_SAS) a2 = __fma_rn(xb, xb, a2); }
     }
 }
 
@@ -255,10 +193,34 @@ __device__ __forceinline__ double row7(const double czm, const double cym, const
 
 // One work item of the TMA SpMV: a 64 x 8 tile column and a z range.  has_u != 0 when the item
 // contains conductor cells (then U tiles and class bytes are staged and the generic row code runs);
-// items without conductor cells run a lean 7-point loop.  Built on the host (build_work_items).
+// items without conductor cells run a lean 7-point loop.  The two kinds are separate kernel
+// instantiations (different register budgets and ring shapes) launched back to back.
 struct WorkItem {
     int x0, y0, kb, ke;     // tile origin, owned planes [kb, ke)
     int has_u, pad0, pad1, pad2;
+};
+
+// Shared-memory stage of the ring.  NIN input tiles (MODE_SAS stages r AND Ap and forms
+// s = r - alpha*Ap on the fly -- solvers.f90:33 fused into the SpMV of :39), each 68 x 10 x 3
+// doubles in a 16 KiB slot; conductor items add the class bytes and NIN U tiles.
+template <int MODE, bool HAS_U>
+struct Stage {
+    static constexpr int NIN = (MODE == MODE_SAS) ? 2 : 1;
+    static constexpr int A_SLOT = 16384;                                  // >= XS_BYTES, 128-byte multiple
+    static constexpr int U_SLOT = 5504;                                   // >= TILE_BYTES, 128-byte multiple
+    static constexpr int CLS_OFF = NIN * A_SLOT;
+    static constexpr int US_OFF = CLS_OFF + (HAS_U ? tma::CLS_BYTES : 0);
+    static constexpr int BYTES = US_OFF + (HAS_U ? NIN * U_SLOT : 0);
+    static constexpr int A2 = A_SLOT / 8, U2 = U_SLOT / 8;                // second input, offset in doubles
+};
+template <int MODE, bool HAS_U>
+constexpr int tma_smem_bytes(int nstage) { return nstage * Stage<MODE, HAS_U>::BYTES + 128; }
+
+struct TmaMaps {            // tensor maps of one launch (by value in kernel parameter space)
+    CUtensorMap xA, xU;     // SpMV input: A part (4-D), dense U box (3-D)
+    CUtensorMap x2A, x2U;   // MODE_SAS: second input (Ap)
+    CUtensorMap cls;        // class bytes
+    CUtensorMap auxA, auxU; // r0 / b: halo-free boxes, L2 prefetch only
 };
 
 struct TmaCtx {             // per-thread constants of k_spmv_tma
@@ -267,43 +229,70 @@ struct TmaCtx {             // per-thread constants of k_spmv_tma
     int o_own, o_cls;
     bool active, inUxy;
     double cxpA, cxmB, cym, cyp, dgA0, dgA1, dgB0, dgB1;
+    double alpha;           // MODE_SAS
 };
+
+// value(s) of the SpMV input at smem position p: the staged vector itself, or (MODE_SAS)
+// s = r - alpha*Ap from the two staged tiles -- same expression, hence same bits, as the s this
+// kernel stores for the owner of that cell
+template <bool SAS>
+__device__ __forceinline__ double in1(const double *p, const int d2, const double alpha)
+{
+    return SAS ? DSUB(p[0], DMUL(alpha, p[d2])) : p[0];
+}
+template <bool SAS>
+__device__ __forceinline__ double2 in2(const double *p, const int d2, const double alpha)
+{
+    const double2 r = *reinterpret_cast<const double2 *>(p);
+    if (!SAS) return r;
+    const double2 q = *reinterpret_cast<const double2 *>(p + d2);
+    return make_double2(DSUB(r.x, DMUL(alpha, q.x)), DSUB(r.y, DMUL(alpha, q.y)));
+}
 
 // Plane loop of one work item.  HAS_U = item contains conductor cells.
 template <int MODE, int NSTAGE, bool HAS_U>
-__device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUtensorMap &tmU, const CUtensorMap &tmC,
-                                               const CUtensorMap &tmAuxA, const CUtensorMap &tmAuxU, const SlabGeom &G,
-                                               const Coef &cf, const MatCoef &mc, const VecSet &vs, const TmaCtx &t,
-                                               unsigned char *smem, unsigned long long *full, unsigned *cnt,
-                                               dd &acc0, dd &acc1)
+__device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom &G, const Coef &cf, const MatCoef &mc,
+                                               const VecSet &vs, const TmaCtx &t, unsigned char *smem,
+                                               unsigned long long *full, unsigned *cnt, dd &acc0, dd &acc1, dd &acc2)
 {
     using namespace tma;
+    using ST = Stage<MODE, HAS_U>;
+    constexpr bool SAS = (MODE == MODE_SAS);
     constexpr bool HAS_AUX = (MODE == MODE_AP || MODE == MODE_INIT);
+    constexpr int A2 = ST::A2, U2 = ST::U2, USD = ST::US_OFF / 8;
     const int ukA = G.ub_k0 - 1, ukB = G.ub_k0 + G.ub_nz;   // U tiles are needed for planes [ukA, ukB]
     const int kb = t.kb, ke = t.ke, nload = t.nload, x0 = t.x0, y0 = t.y0;
     const int sdx = G.sdx, sdz = G.sdz, kdz = G.kdz;
     const int i0 = x0 + 2 * t.tx, j = y0 + t.ty;
     const int o_own = t.o_own;
+    const double alpha = t.alpha;
 
     auto issue = [&](int q) {                               // q-th plane of this item: pl = kb-1+q
         const int pl = kb - 1 + q, s = q % NSTAGE;
-        unsigned char *st = smem + s * STAGE_BYTES;
+        unsigned char *st = smem + s * ST::BYTES;
         const bool u_ = HAS_U && pl >= ukA && pl <= ukB;
         const bool c_ = pl >= kb && pl < ke;                // planes that are computed
-        mbar_expect_tx(full + s, XS_BYTES + (u_ ? TILE_BYTES : 0) + ((HAS_U && c_) ? CLS_BYTES : 0));
-        load4d(st, &tmX, full + s, x0 - 2, y0 - 1, pl - G.k0 + 1, 0);
-        if (u_) load3d(st + US_OFF, &tmU, full + s, x0 - 2 - G.ub_i0, y0 - 1 - G.ub_j0, pl - G.ub_kl0);
-        if (HAS_U && c_) load3d(st + CLS_OFF, &tmC, full + s, x0, y0, pl - G.k0);
+        mbar_expect_tx(full + s, ST::NIN * (XS_BYTES + (u_ ? TILE_BYTES : 0)) + ((HAS_U && c_) ? CLS_BYTES : 0));
+        load4d(st, &tm.xA, full + s, x0 - 2, y0 - 1, pl - G.k0 + 1, 0);
+        if (SAS) load4d(st + ST::A_SLOT, &tm.x2A, full + s, x0 - 2, y0 - 1, pl - G.k0 + 1, 0);
+        if (u_) {
+            load3d(st + ST::US_OFF, &tm.xU, full + s, x0 - 2 - G.ub_i0, y0 - 1 - G.ub_j0, pl - G.ub_kl0);
+            if (SAS) load3d(st + ST::US_OFF + ST::U_SLOT, &tm.x2U, full + s, x0 - 2 - G.ub_i0, y0 - 1 - G.ub_j0, pl - G.ub_kl0);
+        }
+        if (HAS_U && c_) load3d(st + ST::CLS_OFF, &tm.cls, full + s, x0, y0, pl - G.k0);
         if (HAS_AUX && c_) {                                // r0 / b of that plane: pull into L2 ahead of the LDGs
-            prefetch4d(&tmAuxA, x0, y0, pl - G.k0 + 1, 0);      // 64 x 8 x 1 x 3 box, no halo
-            if (u_ && pl > ukA && pl < ukB) prefetch3d(&tmAuxU, x0 - G.ub_i0, y0 - G.ub_j0, pl - G.ub_kl0);
+            prefetch4d(&tm.auxA, x0, y0, pl - G.k0 + 1, 0);     // 64 x 8 x 1 x 3 box, no halo
+            if (u_ && pl > ukA && pl < ukB) prefetch3d(&tm.auxU, x0 - G.ub_i0, y0 - G.ub_j0, pl - G.ub_kl0);
         }
     };
     if (t.warp == 0 && t.lane == 0)
         for (int q = 0; q < min(NSTAGE, nload); ++q) issue(q);
 
     // A warp is done with the tiles of load ql: the last of the 8 warps to say so re-arms that stage
-    // with load ql + NSTAGE.  No CTA-wide barrier: warps drift apart by up to the ring depth.
+    // with load ql + NSTAGE.  No CTA-wide barrier: warps drift apart by up to the ring depth.  The
+    // acq_rel counter orders the other warps' (generic-proxy) reads of the stage before the issuing
+    // thread, and the proxy fence orders them before the copy engine's (async-proxy) refill.
+    // Invariant: ONE work item per CTA -- barrier phases and counters are never reset.
     auto release = [&](int ql) {
         __syncwarp();
         if (t.lane == 0) {
@@ -312,7 +301,7 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
             asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt + s)) : "memory");
             if (old == 7u) {
                 cnt[s] = 0u;
-                if (ql + NSTAGE < nload) issue(ql + NSTAGE);
+                if (ql + NSTAGE < nload) { fence_proxy_async(); issue(ql + NSTAGE); }
             }
         }
     };
@@ -329,15 +318,19 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
 
     auto own_pair = [&](int slot, int q) {                  // wait for load q, read the own pair into `slot`
         mbar_wait(full + s, ph);
-        const double *xn = reinterpret_cast<const double *>(smem + s * STAGE_BYTES);
+        const double *xn = reinterpret_cast<const double *>(smem + s * ST::BYTES);
 #pragma unroll
-        for (int a = 0; a < 3; ++a) pl3[slot][a] = *reinterpret_cast<const double2 *>(xn + a * TILE_D + o_own);
+        for (int a = 0; a < 3; ++a) pl3[slot][a] = in2<SAS>(xn + a * TILE_D + o_own, A2, alpha);
         if (HAS_U) {
             const int pl = kb - 1 + q;
-            ug3[slot] = (pl >= ukA && pl <= ukB) ? *reinterpret_cast<const double2 *>(xn + US_OFF / 8 + o_own) : zero2;
+            ug3[slot] = (pl >= ukA && pl <= ukB) ? in2<SAS>(xn + USD + o_own, U2, alpha) : zero2;
         }
     };
     auto advance = [&]() { if (++s == NSTAGE) { s = 0; ph ^= 1u; } };
+    // U of the dense box straight from global memory (one-sided gradients reach two cells)
+    auto uglob = [&](long long p) -> double {
+        return SAS ? DSUB(vs.x[p], DMUL(alpha, vs.x2[p])) : vs.x[p];
+    };
 
     // loads 0 and 1: planes kb-1, kb
     own_pair(0, 0); advance();
@@ -360,10 +353,10 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
                 const int sprev = (s == 0) ? NSTAGE - 1 : s - 1;
                 // this thread's dot-product terms of plane k: summed in a fixed order here, accumulated
                 // across planes in double-double (independent of how z is cut into items and slabs)
-                double a0 = 0.0, a1 = 0.0;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
                 own_pair(sz_, q);
                 if (t.active) {
-                    const unsigned char *stp = smem + sprev * STAGE_BYTES;
+                    const unsigned char *stp = smem + sprev * ST::BYTES;
                     const double *xs = reinterpret_cast<const double *>(stp);
                     const bool zl = (k == 0), zh = (k == sdz - 1);
                     const double czm = zh ? cf.bhi[2] : cf.msz, czp = zl ? cf.blo[2] : cf.msz;
@@ -379,28 +372,28 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
 #pragma unroll
                         for (int a = 0; a < 3; ++a) {
                             const double *tt = xs + a * TILE_D + o_own;
-                            const double2 ym = *reinterpret_cast<const double2 *>(tt - BW);
-                            const double2 yp = *reinterpret_cast<const double2 *>(tt + BW);
-                            const double xm = tt[-1], xp = tt[2];
+                            const double2 ym = in2<SAS>(tt - BW, A2, alpha);
+                            const double2 yp = in2<SAS>(tt + BW, A2, alpha);
+                            const double xm = in1<SAS>(tt - 1, A2, alpha), xp = in1<SAS>(tt + 2, A2, alpha);
                             const double ya = row7(czm, t.cym, cf.msx, dgA, t.cxpA, t.cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
                             const double yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
-                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2);
                         }
                     } else if (ca == 0x40 && cb == 0x40) {
                         // ---- both cells are interior conductor cells (all six neighbours conductor):
                         //      central grad U in the A rows (EC3D.f90:677-679), 13-entry U rows (:917-922) ----
                         const double2 ugm = ug3[sm_], ugc = ug3[sc_], ugp = ug3[sz_];
-                        const double *tu = xs + US_OFF / 8 + o_own;
-                        const double uxm = tu[-1], uxp = tu[2];
-                        const double2 uym = *reinterpret_cast<const double2 *>(tu - BW);
-                        const double2 uyp = *reinterpret_cast<const double2 *>(tu + BW);
+                        const double *tu = xs + USD + o_own;
+                        const double uxm = in1<SAS>(tu - 1, U2, alpha), uxp = in1<SAS>(tu + 2, U2, alpha);
+                        const double2 uym = in2<SAS>(tu - BW, U2, alpha);
+                        const double2 uyp = in2<SAS>(tu + BW, U2, alpha);
                         double suA = 0.0, suB = 0.0;              // running A part of the U rows
 #pragma unroll
                         for (int a = 0; a < 3; ++a) {
                             const double *tt = xs + a * TILE_D + o_own;
-                            const double2 ym = *reinterpret_cast<const double2 *>(tt - BW);
-                            const double2 yp = *reinterpret_cast<const double2 *>(tt + BW);
-                            const double xm = tt[-1], xp = tt[2];
+                            const double2 ym = in2<SAS>(tt - BW, A2, alpha);
+                            const double2 yp = in2<SAS>(tt + BW, A2, alpha);
+                            const double xm = in1<SAS>(tt - 1, A2, alpha), xp = in1<SAS>(tt + 2, A2, alpha);
                             double ya = row7(mc.cm[2], mc.cm[1], mc.cm[0], mc.diag, mc.cp[0], mc.cp[1], mc.cp[2], m[a].x, ym.x, xm,
                                              c[a].x, c[a].y, yp.x, z1[a].x);
                             double yb = row7(mc.cm[2], mc.cm[1], mc.cm[0], mc.diag, mc.cp[0], mc.cp[1], mc.cp[2], m[a].y, ym.y, c[a].x,
@@ -418,7 +411,7 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
                             const double apB = (a == 0) ? xp : (a == 1) ? yp.y : z1[a].y;
                             suA = DADD(suA, DMUL(cf.ua_p[a], amA)); suA = DADD(suA, DMUL(cf.ua_m[a], apA));
                             suB = DADD(suB, DMUL(cf.ua_p[a], amB)); suB = DADD(suB, DMUL(cf.ua_m[a], apB));
-                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2);
                         }
                         // U columns k-1, j-1, i-1, centre, i+1, j+1, k+1
                         suA = DADD(suA, DMUL(cf.msz, ugm.x)); suB = DADD(suB, DMUL(cf.msz, ugm.y));
@@ -428,37 +421,38 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
                         suA = DADD(suA, DMUL(cf.msx, ugc.y)); suB = DADD(suB, DMUL(cf.msx, uxp));
                         suA = DADD(suA, DMUL(cf.msy, uyp.x)); suB = DADD(suB, DMUL(cf.msy, uyp.y));
                         suA = DADD(suA, DMUL(cf.msz, ugp.x)); suB = DADD(suB, DMUL(cf.msz, ugp.y));
-                        pair_out<MODE>(suA, suB, true, true, pU, ugc.x, ugc.y, auxU, vs, a0, a1);
+                        pair_out<MODE>(suA, suB, true, true, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2);
                     } else {
                         // ---- conductor-surface cells / mixed pairs (never on a domain face): generic per-cell rows ----
                         const double2 ugm = ug3[sm_], ugc = ug3[sc_], ugp = ug3[sz_];
-                        const double *us = xs + US_OFF / 8;
-                        const double *Uin = vs.x;                 // dense U box lives in the input vector
+                        const double *us = xs + USD;
                         U5 ua[3], ub[3];                          // U along x / y / z for cell a / b
                         {
                             const double *tt = us + o_own;
-                            ua[0] = U5{tt[-2], tt[-1], ugc.x, ugc.y, tt[2]};
-                            ub[0] = U5{tt[-1], ugc.x, ugc.y, tt[2], tt[3]};
-                            const double2 um = *reinterpret_cast<const double2 *>(tt - BW);
-                            const double2 up = *reinterpret_cast<const double2 *>(tt + BW);
+                            const double t_m2 = in1<SAS>(tt - 2, U2, alpha), t_m1 = in1<SAS>(tt - 1, U2, alpha);
+                            const double t_p2 = in1<SAS>(tt + 2, U2, alpha), t_p3 = in1<SAS>(tt + 3, U2, alpha);
+                            ua[0] = U5{t_m2, t_m1, ugc.x, ugc.y, t_p2};
+                            ub[0] = U5{t_m1, ugc.x, ugc.y, t_p2, t_p3};
+                            const double2 um = in2<SAS>(tt - BW, U2, alpha);
+                            const double2 up = in2<SAS>(tt + BW, U2, alpha);
                             ua[1] = U5{0.0, um.x, ugc.x, up.x, 0.0};
                             ub[1] = U5{0.0, um.y, ugc.y, up.y, 0.0};
                             ua[2] = U5{0.0, ugm.x, ugc.x, ugp.x, 0.0};
                             ub[2] = U5{0.0, ugm.y, ugc.y, ugp.y, 0.0};
                             // one-sided gradients along y / z reach two cells: read those from the dense box
                             const int sya = (ca >> 2) & 3, syb = (cb >> 2) & 3, sza = (ca >> 4) & 3, szb = (cb >> 4) & 3;
-                            if (sya & 2) ua[1].m2 = Uin[pU - 2 * G.ub_nx]; else if (sya & 1) ua[1].p2 = Uin[pU + 2 * G.ub_nx];
-                            if (syb & 2) ub[1].m2 = Uin[pU + 1 - 2 * G.ub_nx]; else if (syb & 1) ub[1].p2 = Uin[pU + 1 + 2 * G.ub_nx];
-                            if (sza & 2) ua[2].m2 = Uin[pU - 2 * G.ub_pl]; else if (sza & 1) ua[2].p2 = Uin[pU + 2 * G.ub_pl];
-                            if (szb & 2) ub[2].m2 = Uin[pU + 1 - 2 * G.ub_pl]; else if (szb & 1) ub[2].p2 = Uin[pU + 1 + 2 * G.ub_pl];
+                            if (sya & 2) ua[1].m2 = uglob(pU - 2 * G.ub_nx); else if (sya & 1) ua[1].p2 = uglob(pU + 2 * G.ub_nx);
+                            if (syb & 2) ub[1].m2 = uglob(pU + 1 - 2 * G.ub_nx); else if (syb & 1) ub[1].p2 = uglob(pU + 1 + 2 * G.ub_nx);
+                            if (sza & 2) ua[2].m2 = uglob(pU - 2 * G.ub_pl); else if (sza & 1) ua[2].p2 = uglob(pU + 2 * G.ub_pl);
+                            if (szb & 2) ub[2].m2 = uglob(pU + 1 - 2 * G.ub_pl); else if (szb & 1) ub[2].p2 = uglob(pU + 1 + 2 * G.ub_pl);
                         }
                         double suA = 0.0, suB = 0.0;              // running A part of the U rows
 #pragma unroll
                         for (int a = 0; a < 3; ++a) {
                             const double *tt = xs + a * TILE_D + o_own;
-                            const double2 ym = *reinterpret_cast<const double2 *>(tt - BW);
-                            const double2 yp = *reinterpret_cast<const double2 *>(tt + BW);
-                            const double xm = tt[-1], xp = tt[2];
+                            const double2 ym = in2<SAS>(tt - BW, A2, alpha);
+                            const double2 yp = in2<SAS>(tt + BW, A2, alpha);
+                            const double xm = in1<SAS>(tt - 1, A2, alpha), xp = in1<SAS>(tt + 2, A2, alpha);
                             double ya, yb;
                             if (ca) {
                                 const int sa = (ca >> (2 * a)) & 3;
@@ -486,18 +480,19 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
                             } else {
                                 yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
                             }
-                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2);
                         }
                         // U rows
                         double sa_ = 0.0, sb_ = 0.0;
                         if (ca) sa_ = urow_u(cf, ca, ua[2].m1, ua[1].m1, ua[0].m1, ugc.x, ua[0].p1, ua[1].p1, ua[2].p1, suA);
                         if (cb) sb_ = urow_u(cf, cb, ub[2].m1, ub[1].m1, ub[0].m1, ugc.y, ub[0].p1, ub[1].p1, ub[2].p1, suB);
-                        pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1);
+                        pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2);
                     }
                 }
                 if (MODE != MODE_PLAIN) {
                     dd_add_d(acc0, a0);
                     if (MODE != MODE_AP) dd_add_d(acc1, a1);
+                    if (MODE == MODE_SAS) dd_add_d(acc2, a2);
                 }
                 pA += kdz; pU += G.ub_pl;
                 release(q - 1);
@@ -507,13 +502,15 @@ __device__ __forceinline__ void tma_plane_loop(const CUtensorMap &tmX, const CUt
     }
 }
 
-template <int MODE, int NSTAGE>
-__global__ void __launch_bounds__(256, 2)
-k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmU,
-           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAuxA,
-           const __grid_constant__ CUtensorMap tmAuxU, const SlabGeom G, const Coef cf, const MatCoef mc,
+// One launch handles the work items of ONE kind: HAS_U (conductor cells present: U tiles, class
+// bytes, all row rules; CPS = 1 CTA per SM gives it up to 255 registers, no spills) or lean
+// (7-point rows only, CPS >= 2).  Both launches of an SpMV share the reduction ticket: `expected`
+// = items of both, partial index = pbase + blockIdx.x.
+template <int MODE, int NSTAGE, bool HAS_U, int CPS>
+__global__ void __launch_bounds__(256, CPS)
+k_spmv_tma(const __grid_constant__ TmaMaps tm, const SlabGeom G, const Coef cf, const MatCoef mc,
            const WorkItem *__restrict__ items, const VecSet vs, const IterCtl ctl, double *partials, const int pstride,
-           const unsigned expected, const int finalize_here)
+           const int pbase, const unsigned expected)
 {
     using namespace tma;
     extern __shared__ unsigned char smem_raw[];
@@ -538,8 +535,17 @@ k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     t.dgA0 = cf.diag_b[bxyA]; t.dgA1 = cf.diag_b[bxyA | 4];   // diag_b[0] == diag_int
     t.dgB0 = cf.diag_b[bxyB]; t.dgB1 = cf.diag_b[bxyB | 4];
     t.o_own = (t.ty + 1) * BW + 2 + 2 * t.tx;               // own pair inside a halo tile (doubles)
-    t.o_cls = CLS_OFF + t.ty * TX + 2 * t.tx;               // own pair's class bytes inside a stage
+    t.o_cls = Stage<MODE, HAS_U>::CLS_OFF + t.ty * TX + 2 * t.tx;   // own pair's class bytes inside a stage
     t.inUxy = t.active && i0 >= G.ub_i0 && i0 < G.ub_i0 + G.ub_nx && j >= G.ub_j0 && j < G.ub_j0 + G.ub_ny;
+    t.alpha = 0.0;
+    if (MODE == MODE_SAS) {
+        // alpha = rr0/(AP,R0)   solvers.f90:31-32 (every thread derives it from the device scalars)
+        const Scal *sc = ctl.sc;
+        const int it = *ctl.iter_base + ctl.it_off;
+        const double rr0 = (it == 1) ? sc->red[RED_RR_INIT] : sc->rr0[it & 1];
+        t.alpha = rr0 / sc->red[RED_APR0];
+        if (is_block0()) ctl.sc->alpha = t.alpha;
+    }
 
     if (t.warp == 0 && t.lane == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); cnt[s] = 0u; }
@@ -548,19 +554,19 @@ k_spmv_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
     __syncthreads();
 
-    dd a0 = dd_zero(), a1 = dd_zero();
-    if (w.has_u) tma_plane_loop<MODE, NSTAGE, true>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
-    else         tma_plane_loop<MODE, NSTAGE, false>(tmX, tmU, tmC, tmAuxA, tmAuxU, G, cf, mc, vs, t, smem, full, cnt, a0, a1);
+    dd a0 = dd_zero(), a1 = dd_zero(), a2 = dd_zero();
+    tma_plane_loop<MODE, NSTAGE, HAS_U>(tm, G, cf, mc, vs, t, smem, full, cnt, a0, a1, a2);
 
     if (MODE != MODE_PLAIN) {
-        const int pidx = blockIdx.x;
-        const unsigned ex = finalize_here ? expected : 0xffffffffu;
+        const int pidx = pbase + blockIdx.x;
         if (MODE == MODE_AP)
-            reduce_epilogue<1>(a0, dd_zero(), partials, pstride, pidx, ex, ctl.sc, RED_APR0, RED_APR0, sh);
+            reduce_epilogue<1>(a0, dd_zero(), dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_APR0, RED_APR0, RED_APR0, sh);
         else if (MODE == MODE_AS)
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, ex, ctl.sc, RED_ASS, RED_ASAS, sh);
+            reduce_epilogue<2>(a0, a1, dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, RED_ASAS, sh);
+        else if (MODE == MODE_SAS)
+            reduce_epilogue<3>(a0, a1, a2, partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, RED_SS, sh);
         else
-            reduce_epilogue<2>(a0, a1, partials, pstride, pidx, ex, ctl.sc, RED_BB, RED_RR_INIT, sh);
+            reduce_epilogue<2>(a0, a1, dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_BB, RED_RR_INIT, RED_RR_INIT, sh);
     }
 }
 

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libec3d_gpu.so")
 
 EXPORTS = [
-    "sprsbcgstabwr_", "ec3d_bicgstabwr_csr", "ec3d_csr_cache_clear", "ec3d_nccl_unique_id",
+    "sprsbcgstabwr_", "SPRSBCGSTABWR", "ec3d_bicgstabwr_csr", "ec3d_csr_cache_clear", "ec3d_nccl_unique_id",
     "ec3d_create", "ec3d_destroy", "ec3d_sizes", "ec3d_assemble_csr", "ec3d_step", "ec3d_step_stage",
     "ec3d_get_fields", "ec3d_set_fields", "ec3d_get_vtk_fields", "ec3d_get_source_cells", "ec3d_apply_operator",
     "ec3d_solve_host", "ec3d_bench_kernel", "ec3d_counters", "ec3d_timer_start", "ec3d_timer_stop", "ec3d_global_launch_count",
@@ -28,10 +28,9 @@ EXPORTS = [
 # (which, kernel, algorithmic bytes per owned unknown, per owned cell, what it replaces in solvers.f90)
 KERNELS = [
     (0, "k_spmv_tma<AP>", 24.0, 5.0, "AP = A*P fused with (AP,R0), solvers.f90:30-32"),
-    (2, "k_s_update", 24.0, 0.0, "S = R - alpha*AP, ||S||^2, solvers.f90:33-34"),
-    (1, "k_spmv_tma<AS>", 16.0, 5.0, "AS = A*S fused with (AS,S), (AS,AS), solvers.f90:39-40"),
-    (3, "k_xr_update", 56.0, 0.0, "X += alpha*P + omega*S; R = S - omega*AS; ||R||^2; (R,R0), solvers.f90:41-44"),
-    (4, "k_p_update", 32.0, 0.0, "exit tests, beta, P = R + beta*(P - omega*AP), restart, solvers.f90:43-49"),
+    (1, "k_spmv_tma<SAS>", 32.0, 5.0, "S = R - alpha*AP fused into AS = A*S with ||S||^2, (AS,S), (AS,AS), solvers.f90:33-40"),
+    (3, "k_xr_update_tma", 56.0, 0.0, "X += alpha*P + omega*S; R = S - omega*AS; ||R||^2; (R,R0), solvers.f90:41-44"),
+    (4, "k_p_update_tma", 32.0, 0.0, "exit tests, beta, P = R + beta*(P - omega*AP), restart, solvers.f90:43-49"),
 ]
 
 
@@ -67,6 +66,8 @@ def load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} not built: run __graft_entry__.build() "
                           "(nvcc -gencode arch=compute_100a,code=sm_100a); there is no CPU fallback")
+    # this host raises Ec3dError on failures; the Fortran symbol aborts instead (no status argument exists)
+    os.environ.setdefault("EC3D_NO_ABORT", "1")
     L = C.CDLL(LIB_PATH)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     L.sprsbcgstabwr_.restype = None

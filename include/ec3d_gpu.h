@@ -47,9 +47,16 @@ enum {
  * (0 and x untouched when ||b|| == 0), up to itmax+1 iterations, on non-convergence the residual
  * norm is printed to stdout and the call returns normally.  The CSR arrays are immutable during a
  * run, so a device copy is cached and reused while (pointers, n, nnz) stay the same.
- * On a CUDA failure the message goes to stderr and iter is set to -1. */
+ * The device copy is keyed on a content hash of irow / jcol / valA (one host pass per call), so a
+ * re-assembled matrix in the same arrays is uploaded again (values only when the sparsity is unchanged).
+ * On a CUDA failure the message goes to stderr and the process ABORTS: the interface has no status
+ * argument and the reference's host ignores iter (EC3D.f90:408), so returning would let it time-step on
+ * a stale x.  (EC3D_NO_ABORT=1 in the environment: iter = -1 and return; the Python binding sets it and
+ * raises.)  SPRSBCGSTABWR is the same procedure under ifort / Windows mangling (reference Makefile:30-47). */
 void sprsbcgstabwr_(double *valA, int32_t *irow, int32_t *jcol, int32_t *n, double *b, double *x,
                     double *tolerance, int32_t *itmax, int32_t *iter);
+void SPRSBCGSTABWR(double *valA, int32_t *irow, int32_t *jcol, int32_t *n, double *b, double *x,
+                   double *tolerance, int32_t *itmax, int32_t *iter);
 
 /* Same operation for ISO_C_BINDING callers; returns a status code. */
 int ec3d_bicgstabwr_csr(const double *valA, const int32_t *irow, const int32_t *jcol, int32_t n,
@@ -162,9 +169,11 @@ int ec3d_solve_host(ec3d_handle *h, const double *b, double *x, int32_t *iter);
 /* ------------------------------------------------------------------------------------------ */
 
 /* Times `reps` launches of one kernel class with CUDA events on the library's stream after
- * `warm` untimed launches; writes the mean ms per launch.  which: 0 = stencil SpMV fused with
- * (Ap,r0); 1 = stencil SpMV fused with (As,s),(As,As); 2 = s = r - alpha*Ap with ||s||^2;
- * 3 = x,r update with 2 dots; 4 = p update; 5 = one whole BiCGSTABwr iteration (no exit). */
+ * `warm` untimed launches; writes the mean ms per launch.  which: 0 = stencil SpMV A*p fused with
+ * (Ap,r0); 1 = stencil SpMV A*s fused with s = r - alpha*Ap, ||s||^2, (As,s), (As,As) (the unfused
+ * A*s kernel when the s-update is not fused: odd grids, EC3D_FUSE_S=0); 2 = stand-alone
+ * s = r - alpha*Ap with ||s||^2; 3 = x,r update with 2 dots; 4 = p update; 5 = one whole BiCGSTABwr
+ * iteration, every kernel in sequence without exit (single rank only). */
 int ec3d_bench_kernel(ec3d_handle *h, int32_t which, int32_t warm, int32_t reps, double *ms);
 
 /* Counters since creation: kernels launched by this library, solver iterations, and device ms

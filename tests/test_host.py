@@ -94,7 +94,7 @@ def test_library_exports_every_header_symbol():
     L = lib.load()
     hdr = open(os.path.join(ROOT, "include", "ec3d_gpu.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    names = set(re.findall(r"\b(ec3d_[a-z0-9_]+|sprsbcgstabwr_)\s*\(", hdr))
+    names = set(re.findall(r"\b(ec3d_[a-z0-9_]+|sprsbcgstabwr_|SPRSBCGSTABWR)\s*\(", hdr))
     assert len(names) >= 20
     for nm in sorted(names):
         assert hasattr(L, nm), nm
