@@ -614,6 +614,8 @@ struct ec3d_handle {
     // timing
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_t[2] = {nullptr, nullptr};
+    cudaStream_t st2 = nullptr;                  // side stream: lean SpMV items run beside the conductor items
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double last_step_ms = 0.0, last_solve_ms = 0.0;
     long long launches = 0;
 };
@@ -696,12 +698,12 @@ template <int MODE> struct RingCfg {
 };
 
 template <int MODE, int NSTAGE, bool HAS_U, int CPS>
-static void launch_tma_kind(ec3d_handle *h, const TmaMaps &tm, const WorkItem *items, int nitems, int pbase, unsigned expected,
-                            const VecSet &vs, const IterCtl &ctl)
+static void launch_tma_kind(ec3d_handle *h, cudaStream_t st, const TmaMaps &tm, const WorkItem *items, int nitems, int pbase,
+                            unsigned expected, const VecSet &vs, const IterCtl &ctl)
 {
     if (nitems <= 0) return;
     Solver &s = h->sol;
-    k_spmv_tma<MODE, NSTAGE, HAS_U, CPS><<<nitems, dim3(32, 8), tma_smem_bytes<MODE, HAS_U>(NSTAGE), h->st>>>(
+    k_spmv_tma<MODE, NSTAGE, HAS_U, CPS><<<nitems, dim3(32, 8), tma_smem_bytes<MODE, HAS_U>(NSTAGE), st>>>(
         tm, h->G, h->cf, h->mc0, items, vs, ctl, s.partials, s.pstride, pbase, expected);
     g_launches.fetch_add(1);
 }
@@ -724,14 +726,27 @@ static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
         tm.auxA = h->tmPA[va]; tm.auxU = h->tmPU[va];
         const unsigned expected = (unsigned)(h->nitems_cond + h->nitems_lean);
         int nl = 0;
+        // The two kinds run CONCURRENTLY (fork / join on a side stream; parallel branches when captured
+        // into the iteration graph): lean CTAs fill the SMs the conductor kernel's last wave leaves idle.
+        // They write disjoint rows and share the reduction ticket, so no order between them matters.
+        const bool fork = h->nitems_cond && h->nitems_lean && h->st2;
+        cudaStream_t stl = fork ? h->st2 : h->st;
+        if (fork) {
+            cudaEventRecord(h->ev_fork, h->st);
+            cudaStreamWaitEvent(h->st2, h->ev_fork, 0);
+        }
         if (h->nitems_cond) {
-            if (h->ccps == 1) launch_tma_kind<MODE, RingCfg<MODE>::COND1, true, 1>(h, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
-            else              launch_tma_kind<MODE, RingCfg<MODE>::COND2, true, 2>(h, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
+            if (h->ccps == 1) launch_tma_kind<MODE, RingCfg<MODE>::COND1, true, 1>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
+            else              launch_tma_kind<MODE, RingCfg<MODE>::COND2, true, 2>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
             ++nl;
         }
         if (h->nitems_lean) {
-            launch_tma_kind<MODE, RingCfg<MODE>::LEAN, false, 2>(h, tm, h->d_items + h->nitems_cond, h->nitems_lean, h->nitems_cond, expected, vs, ctl);
+            launch_tma_kind<MODE, RingCfg<MODE>::LEAN, false, 2>(h, stl, tm, h->d_items + h->nitems_cond, h->nitems_lean, h->nitems_cond, expected, vs, ctl);
             ++nl;
+        }
+        if (fork) {
+            cudaEventRecord(h->ev_join, h->st2);
+            cudaStreamWaitEvent(h->st, h->ev_join, 0);
         }
         return nl;
     }
@@ -789,6 +804,9 @@ extern "C" int ec3d_destroy(ec3d_handle *h)
     if (h->h_src) cudaFreeHost(h->h_src);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->st2) cudaStreamDestroy(h->st2);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return EC3D_OK;
@@ -1045,6 +1063,7 @@ static int set_tma_smem_attr()
 {
     CUDA_TRY(set_attr_mode<MODE_PLAIN>());
     CUDA_TRY(set_attr_mode<MODE_AP>());
+    CUDA_TRY(set_attr_mode<MODE_AS>());
     CUDA_TRY(set_attr_mode<MODE_INIT>());
     CUDA_TRY(set_attr_mode<MODE_SAS>());
     return EC3D_OK;
@@ -1077,6 +1096,14 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     for (auto &e : h->ev) CUDA_TRY(cudaEventCreate(&e));
     for (auto &e : h->ev_t) CUDA_TRY(cudaEventCreate(&e));
+    {
+        const char *e2 = getenv("EC3D_FORK");
+        if (!(e2 && atoi(e2) == 0)) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+    }
 
     // ---- slab partition ----
     std::vector<long long> cpp(sdz, 0);          // conductor cells per plane
@@ -1090,6 +1117,18 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         std::vector<int64_t> cpp64(cpp.begin(), cpp.end());
         int rc = ec3d_partition_planes(sdx, sdy, sdz, cpp64.data(), h->nranks, kstart.data());
         if (rc) return rc;
+        // EC3D_KSTART="k1,k2,..." (first plane of ranks 1..nranks-1): explicit cuts, used by the tests to put
+        // a slab boundary exactly on a conductor face / to make conductor-free slabs
+        const char *ek = getenv("EC3D_KSTART");
+        if (ek && h->nranks > 1) {
+            std::vector<int> ks(1, 0);
+            for (const char *q = ek; *q;) { ks.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+            ks.push_back(sdz);
+            bool ok = (int)ks.size() == h->nranks + 1;
+            for (size_t r = 0; ok && r + 1 < ks.size(); ++r) ok = ks[r + 1] - ks[r] >= 2;
+            if (!ok) { ec3d_set_error("EC3D_KSTART needs nranks-1 increasing cuts, >= 2 planes per slab"); return EC3D_ERR_ARG; }
+            kstart = ks;
+        }
     }
     SlabGeom &G = h->G;
     memset(&G, 0, sizeof(G));

@@ -135,6 +135,132 @@ done:
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Bridge solver: the SAME algorithm (solvers.f90:3-50) with EXACTLY ROUNDED inner products.      */
+/*                                                                                                */
+/* The CUDA path cannot reproduce the rounding errors of the reference's sequential DOT_PRODUCT / */
+/* NORM2 (a serial recurrence); it sums the products in double-double instead, i.e. it returns    */
+/* the correctly rounded value of the sum of its product terms.  This function does the same on   */
+/* the CPU, with the same definition of the product terms:                                        */
+/*   F(v,w)  dots fused into the stencil SpMV -- one term per x-adjacent cell pair (i even) and   */
+/*           plane: fma chain over Ax(a),Ax(b),Ay(a),Ay(b),Az(a),Az(b),U(a),U(b) starting from 0  */
+/*   B(v,w)  dots of the vector-update kernels -- one term per x-adjacent cell pair and           */
+/*           component: fma(v_b, w_b, v_a*w_a)                                                    */
+/* and the same reuse of (R,R0): rr0 of iteration i+1 is rr0_new of iteration i (||R||^2 after a  */
+/* restart, ||R||^2 from the initial residual in iteration 1) instead of a recomputed dot product. */
+/* Every vector operation and the SpMV are the reference's, unchanged.  The tests use it as the   */
+/* bridge: CUDA == bridge bit for bit, and bridge vs orc_sprsBCGstabWR isolates what the          */
+/* reference's own summation error does to its iterates.  Needs even sdx (the CUDA main path).    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { double hi, lo; } orc_dd;
+static inline void dd_add(orc_dd *a, double b)
+{
+    double s = a->hi + b;
+    double bb = s - a->hi;
+    double e = (a->hi - (s - bb)) + (b - bb);
+    a->hi = s;
+    a->lo += e;
+}
+
+typedef struct {
+    int32_t sdx, sdy, sdz;
+    int64_t nC;
+    const int32_t *geoC;
+} xd_grid;
+
+static double xd_F(const xd_grid *g, const double *v, const double *w)
+{
+    orc_dd acc = {0.0, 0.0};
+    const int64_t nC = g->nC;
+    for (int64_t c0 = 0; c0 < nC; c0 += 2) {            /* sdx even: (c0, c0+1) are x-adjacent, same j,k */
+        double t = 0.0;
+        for (int comp = 0; comp < 3; ++comp) {
+            t = fma(v[comp * nC + c0], w[comp * nC + c0], t);
+            t = fma(v[comp * nC + c0 + 1], w[comp * nC + c0 + 1], t);
+        }
+        const int32_t ga = g->geoC[c0], gb = g->geoC[c0 + 1];
+        if (ga) t = fma(v[ga - 1], w[ga - 1], t);
+        if (gb) t = fma(v[gb - 1], w[gb - 1], t);
+        dd_add(&acc, t);
+    }
+    return acc.hi + acc.lo;
+}
+
+static double xd_B(const xd_grid *g, const double *v, const double *w)
+{
+    orc_dd acc = {0.0, 0.0};
+    const int64_t nC = g->nC;
+    for (int comp = 0; comp < 3; ++comp)
+        for (int64_t c0 = 0; c0 < nC; c0 += 2)
+            dd_add(&acc, fma(v[comp * nC + c0 + 1], w[comp * nC + c0 + 1], v[comp * nC + c0] * w[comp * nC + c0]));
+    for (int64_t c0 = 0; c0 < nC; c0 += 2) {
+        const int32_t ga = g->geoC[c0], gb = g->geoC[c0 + 1];
+        if (!ga && !gb) continue;
+        const double va = ga ? v[ga - 1] : 0.0, wa = ga ? w[ga - 1] : 0.0;
+        const double vb = gb ? v[gb - 1] : 0.0, wb = gb ? w[gb - 1] : 0.0;
+        dd_add(&acc, fma(vb, wb, va * wa));
+    }
+    return acc.hi + acc.lo;
+}
+
+int orc_sprsBCGstabWR_exact_dots(const double *valA, const int32_t *irow, const int32_t *jcol, int32_t n,
+                                 const double *b, double *x, double tolerance, int32_t itmax, int32_t *iter,
+                                 int32_t sdx, int32_t sdy, int32_t sdz, const int32_t *geoPHYS_C)
+{
+    if (sdx % 2 != 0) return -2;
+    const xd_grid g = {sdx, sdy, sdz, (int64_t)sdx * sdy * sdz, geoPHYS_C};
+    double alpha, beta, omega, rr0, rr0_next = 0.0, rr = 0.0;
+    size_t nb = (size_t)n * sizeof(double);
+    double *R = malloc(nb), *R0 = malloc(nb), *P = malloc(nb), *AP = malloc(nb), *S = malloc(nb),
+           *AS = malloc(nb);
+    if (!R || !R0 || !P || !AP || !S || !AS) {
+        free(R); free(R0); free(P); free(AP); free(S); free(AS);
+        return -1;
+    }
+    *iter = 0;
+    orc_sprsAx(valA, irow, jcol, n, x, R);
+    for (int32_t j = 0; j < n; ++j) R[j] = b[j] - R[j];
+    memcpy(R0, R, nb);
+    memcpy(P, R, nb);
+    const double bb = xd_F(&g, b, b), rr_init = xd_F(&g, R, R);
+    const double Bnorm = sqrt(bb);
+    if (bb == 0.0) goto done;
+    for (;;) {
+        if (*iter > itmax) {
+            printf(" %24.16E\n", sqrt(rr));
+            break;
+        }
+        *iter += 1;
+        orc_sprsAx(valA, irow, jcol, n, P, AP);
+        rr0 = (*iter == 1) ? rr_init : rr0_next;
+        alpha = rr0 / xd_F(&g, AP, R0);
+        for (int32_t j = 0; j < n; ++j) S[j] = R[j] - alpha * AP[j];
+        orc_sprsAx(valA, irow, jcol, n, S, AS);
+        if (sqrt(xd_F(&g, S, S)) / Bnorm < tolerance) {
+            for (int32_t j = 0; j < n; ++j) x[j] = x[j] + alpha * P[j];
+            break;
+        }
+        omega = xd_F(&g, AS, S) / xd_F(&g, AS, AS);
+        for (int32_t j = 0; j < n; ++j) x[j] = x[j] + alpha * P[j] + omega * S[j];
+        for (int32_t j = 0; j < n; ++j) R[j] = S[j] - omega * AS[j];
+        rr = xd_B(&g, R, R);
+        if (sqrt(rr) / Bnorm < tolerance) break;
+        const double rr0_new = xd_B(&g, R, R0);
+        beta = (alpha / omega) * rr0_new / rr0;
+        const int restart = (fabs(rr0_new) / Bnorm) < tolerance;
+        rr0_next = restart ? rr : rr0_new;
+        if (restart) {
+            memcpy(R0, R, nb);
+            memcpy(P, R, nb);
+        } else {
+            for (int32_t j = 0; j < n; ++j) P[j] = R[j] + beta * (P[j] - omega * AP[j]);
+        }
+    }
+done:
+    free(R); free(R0); free(P); free(AP); free(S); free(AS);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* utilites.f90:477-508  full_sort(a,b,n,1,1): repeated adjacent-swap passes, ascending column  */
 /* ------------------------------------------------------------------------------------------ */
 static void full_sort(int32_t *a, double *b, int n)

@@ -63,6 +63,15 @@ int orc_gen_sparse_matrix(const orc_grid *g, orc_csr *out);
 int orc_sprsBCGstabWR(const double *valA, const int32_t *irow, const int32_t *jcol, int32_t n,
                       const double *b, double *x, double tolerance, int32_t itmax, int32_t *iter);
 
+/* Bridge between the reference and the CUDA path: solvers.f90:3-50 with EXACTLY ROUNDED inner
+ * products (double-double sums of the product terms the CUDA kernels form, see ec3d_oracle.c) and
+ * every vector operation / SpMV as in the reference.  The CUDA path must equal THIS bit for bit; its
+ * distance to orc_sprsBCGstabWR is what the reference's own summation error does to its iterates.
+ * Needs the grid (even sdx) to know the cell pairs.  Returns 0, -2 for odd sdx. */
+int orc_sprsBCGstabWR_exact_dots(const double *valA, const int32_t *irow, const int32_t *jcol, int32_t n,
+                                 const double *b, double *x, double tolerance, int32_t itmax, int32_t *iter,
+                                 int32_t sdx, int32_t sdy, int32_t sdz, const int32_t *geoPHYS_C);
+
 /* solvers.f90:54-61 */
 void orc_sprsAx(const double *valA, const int32_t *irow, const int32_t *jcol, int32_t n,
                 const double *v, double *y);

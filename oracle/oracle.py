@@ -71,6 +71,10 @@ def lib():
         L.orc_sprsBCGstabWR.restype = C.c_int
         L.orc_sprsBCGstabWR.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_double, C.c_int32, C.POINTER(C.c_int32)]
+        L.orc_sprsBCGstabWR_exact_dots.restype = C.c_int
+        L.orc_sprsBCGstabWR_exact_dots.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                                   C.c_void_p, C.c_double, C.c_int32, C.POINTER(C.c_int32),
+                                                   C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.orc_sprsAx.restype = None
         L.orc_sprsAx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_set_dot_mode.restype = None
@@ -126,6 +130,19 @@ def bicgstabwr(valA, irow, jcol, b, x, tolerance: float, itmax: int) -> int:
                                  float(tolerance), int(itmax), C.byref(it))
     if rc != 0:
         raise MemoryError("oracle solver allocation failed")
+    return it.value
+
+
+def bicgstabwr_exact_dots(valA, irow, jcol, b, x, tolerance: float, itmax: int, problem) -> int:
+    """The bridge solver (see ec3d_oracle.h): solvers.f90:3-50 with exactly rounded inner products."""
+    assert x.dtype == np.float64 and x.flags.c_contiguous
+    g = np.ascontiguousarray(problem.geoPHYS_C, np.int32)
+    it = C.c_int32(0)
+    rc = lib().orc_sprsBCGstabWR_exact_dots(_p(valA), _p(irow), _p(jcol), irow.size - 1, _p(b), _p(x),
+                                            float(tolerance), int(itmax), C.byref(it),
+                                            problem.sdx, problem.sdy, problem.sdz, _p(g))
+    if rc != 0:
+        raise RuntimeError(f"bridge solver failed (rc={rc}; -2: odd sdx)")
     return it.value
 
 
@@ -208,9 +225,10 @@ class Assembled:
 class OracleRun:
     """The reference's main program (EC3D.f90:93-455) over the oracle subroutines."""
 
-    def __init__(self, problem, assembled: Optional[Assembled] = None):
+    def __init__(self, problem, assembled: Optional[Assembled] = None, exact_dots: bool = False):
         p = problem
         self.p = p
+        self.exact_dots = exact_dots          # True: the bridge solver instead of the reference's reductions
         self.A = assembled if assembled is not None else Assembled(p)
         if self.A.rc != 0:
             raise RuntimeError(f"gen_sparse_matrix: reference would STOP (rc={self.A.rc}, "
@@ -267,7 +285,9 @@ class OracleRun:
         L.orc_rhs_pre(C.byref(self.A.grid), C.byref(self.cond), C.byref(self.A.csr), _p(self.Uaf), _p(self.Jaf))
         self.rhs = self.Jaf.copy()
         it = 0
-        if solve:
+        if solve and self.exact_dots:
+            it = bicgstabwr_exact_dots(self.A.valA, self.A.irow, self.A.jcol, self.Jaf, self.Uaf, p.tolerance, p.itmax, p)
+        elif solve:
             it = bicgstabwr(self.A.valA, self.A.irow, self.A.jcol, self.Jaf, self.Uaf, p.tolerance, p.itmax)
         L.orc_rhs_post(C.byref(self.A.grid), C.byref(self.cond), C.byref(self.A.csr), _p(self.Uaf), _p(self.Jaf))
         self.iters.append(it)

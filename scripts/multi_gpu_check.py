@@ -70,7 +70,9 @@ def main():
             # first step: north-star bars against the oracle; later steps: iteration counts within 5 % (the
             # fields drift with the oracle's own summation-order sensitivity, see tests/test_gpu_parity.py);
             # at every step the multi-GPU fields must equal the single-GPU ones bit for bit
-            if abs(it_g - it_o) > max(1, int(np.ceil(0.05 * it_o))) or (s == 0 and (eu > 1e-8 or ej > 1e-8)):
+            # (plate(64): the reference's own reassociation sensitivity exceeds 1e-9 already in step 0, see
+            # profiles/r02_parity_table.md; this script is used with plate(32) / the decks)
+            if abs(it_g - it_o) > max(1, int(np.ceil(0.05 * it_o))) or (s == 0 and (eu > 1e-9 or ej > 1e-9)):
                 ok = False
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
