@@ -156,6 +156,11 @@ struct Solver {
     std::function<int(int slot, int count)> allreduce;  // sum sc->red[slot..slot+count) over ranks
     bool multi = false;
     bool p2p = false;                                   // exchanges are plain kernels: graph capture allowed
+    bool xfused = false;                                // exchanges live INSIDE the compute kernels (ec3d_comm.cuh)
+    PeerTable pt{};                                     // (zero when single rank)
+    CommLocal *cl = nullptr;
+    double *vecs_base = nullptr;                        // vector allocation and stride: vector index of a pointer
+    long long vstride = 1;
     bool x_halo_fresh = false;                          // the caller just exchanged the halo of X
     // graph of `graph_chunk` iterations
     cudaGraphExec_t graph = nullptr;
@@ -168,9 +173,13 @@ struct Solver {
     int predicted = 0;                                  // iteration count of the previous solve
 };
 
-static VecSet vecset_ap(const Solver &s) { return VecSet{s.P, s.AP, s.R0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; }
-static VecSet vecset_as(const Solver &s) { return VecSet{s.S, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; }
-static VecSet vecset_sas(const Solver &s) { return VecSet{s.R, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr, s.AP, s.S}; }
+static int vec_index(const Solver &s, const double *v) { return (v && s.vecs_base) ? (int)((v - s.vecs_base) / s.vstride) : 0; }
+static VecSet vecset_ap(const Solver &s)
+{
+    return VecSet{s.P, s.AP, s.R0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, vec_index(s, s.AP), 0, 0};
+}
+static VecSet vecset_as(const Solver &s) { return VecSet{s.S, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0}; }
+static VecSet vecset_sas(const Solver &s) { return VecSet{s.R, s.AS, nullptr, nullptr, nullptr, nullptr, nullptr, s.AP, s.S, 0, 0, 0}; }
 
 static void launch_s_update(Solver &s, const IterCtl &ctl)
 {
@@ -190,7 +199,8 @@ static void launch_xr_update(Solver &s, double *X, const IterCtl &ctl)
     const SlabGeom &G = s.G;
     if (s.ring) {
         const unsigned nb = (unsigned)s.nblkRingXR;
-        k_xr_update_tma<<<nb, 256, v1_smem_bytes(5, XR_NST), s.st>>>(G, X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
+        k_xr_update_tma<<<nb, 256, v1_smem_bytes(5, XR_NST), s.st>>>(G, X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb,
+                                                                      s.pt, s.cl, s.xfused ? 1 : 0, vec_index(s, s.R));
     } else {
         const unsigned nb = (unsigned)s.nblkVec;
         if (s.vec == 2) k_xr_update<2><<<nb, 256, 0, s.st>>>(G, X, s.P, s.S, s.AS, s.R, s.R0, ctl, s.partials, s.pstride, nb);
@@ -202,7 +212,8 @@ static void launch_p_update(Solver &s, const IterCtl &ctl)
 {
     const SlabGeom &G = s.G;
     if (s.ring) {
-        k_p_update_tma<<<(unsigned)s.nblkRingP, 256, v1_smem_bytes(3, P_NST), s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
+        k_p_update_tma<<<(unsigned)s.nblkRingP, 256, v1_smem_bytes(3, P_NST), s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl, s.pt, s.cl,
+                                                                                       s.xfused ? 1 : 0, vec_index(s, s.P));
     } else {
         const unsigned nb = (unsigned)s.nblkVec;
         if (s.vec == 2) k_p_update<2><<<nb, 256, 0, s.st>>>(G, s.P, s.R, s.AP, s.R0, ctl);
@@ -216,23 +227,24 @@ static void launch_p_update(Solver &s, const IterCtl &ctl)
 static int solver_enqueue_iteration(Solver &s, int it_off)
 {
     const IterCtl ctl{s.sc, s.iter_base, it_off};
-    if (s.multi) { int rc = s.halo(s.P, nullptr, 1); if (rc) return rc; }
+    const bool xl = s.multi && !s.xfused;              // stand-alone exchange launches (NCCL / un-fused fallback)
+    if (xl) { int rc = s.halo(s.P, nullptr, 1); if (rc) return rc; }
     s.launches += s.spmv(MODE_AP, vecset_ap(s), ctl);                 // AP = A*P, (AP,R0)      solvers.f90:30-32
-    if (s.multi) { int rc = s.allreduce(RED_APR0, 1); if (rc) return rc; }
+    if (xl) { int rc = s.allreduce(RED_APR0, 1); if (rc) return rc; }
     if (s.fused_sas) {
-        if (s.multi) { int rc = s.halo(s.R, s.AP, 1); if (rc) return rc; }
+        if (xl) { int rc = s.halo(s.R, s.AP, 1); if (rc) return rc; }
         // S = R - alpha*AP; AS = A*S; ||S||^2, (AS,S), (AS,AS)        solvers.f90:33-40 (AS is speculative:
         // when ||S|| passes the test of :34 the x-update below takes the exit and AS is never used)
         s.launches += s.spmv(MODE_SAS, vecset_sas(s), ctl);
-        if (s.multi) { int rc = s.allreduce(RED_SS, 3); if (rc) return rc; }
+        if (xl) { int rc = s.allreduce(RED_SS, 3); if (rc) return rc; }
     } else {
         launch_s_update(s, ctl);
-        if (s.multi) { int rc = s.allreduce(RED_SS, 1); if (rc) return rc; rc = s.halo(s.S, nullptr, 1); if (rc) return rc; }
+        if (xl) { int rc = s.allreduce(RED_SS, 1); if (rc) return rc; rc = s.halo(s.S, nullptr, 1); if (rc) return rc; }
         s.launches += s.spmv(MODE_AS, vecset_as(s), ctl);             // AS = A*S, (AS,S), (AS,AS)  solvers.f90:39-40
-        if (s.multi) { int rc = s.allreduce(RED_ASS, 2); if (rc) return rc; }
+        if (xl) { int rc = s.allreduce(RED_ASS, 2); if (rc) return rc; }
     }
     launch_xr_update(s, s.X, ctl);
-    if (s.multi) { int rc = s.allreduce(RED_RR, 2); if (rc) return rc; }
+    if (xl) { int rc = s.allreduce(RED_RR, 2); if (rc) return rc; }
     launch_p_update(s, ctl);
     return EC3D_OK;
 }
@@ -294,11 +306,11 @@ static int solver_run(Solver &s, const double *B, double tol, int itmax, int *it
     if (s.multi && !s.x_halo_fresh) { int rc = s.halo(s.X, nullptr, 0); if (rc) return rc; }
     s.x_halo_fresh = false;
     {   // R = B - A*X; R0 = R; P = R; ||b||^2; (R,R0)               solvers.f90:13-21
-        VecSet vs{s.X, nullptr, nullptr, B, s.R, s.R0, s.P, nullptr, nullptr};
+        VecSet vs{s.X, nullptr, nullptr, B, s.R, s.R0, s.P, nullptr, nullptr, 0, vec_index(s, s.R), vec_index(s, s.P)};
         const IterCtl ctl{s.sc, s.iter_base, 0};
         s.launches += s.spmv(MODE_INIT, vs, ctl);
     }
-    if (s.multi) { int rc = s.allreduce(RED_BB, 2); if (rc) return rc; }
+    if (s.multi && !s.xfused) { int rc = s.allreduce(RED_BB, 2); if (rc) return rc; }
     const long long cap = (long long)itmax + 2;       // the reference runs at most itmax+1 iterations
     long long enq = 0;
     int chunk = s.graph ? s.graph_chunk : 8;
@@ -566,7 +578,7 @@ struct ec3d_handle {
     int mat0 = 0;
     MatCoef mc0{};
     bool tma = false;                    // k_spmv_tma usable (even sdx); else k_air_spmv + k_cond_spmv
-    int ccps = 2;                        // CTAs per SM of the conductor-item kernel (EC3D_CCPS = 1 | 2)
+    int ccps = 0;                        // CTAs per SM of the conductor-item kernel (EC3D_CCPS = 1 | 2; 0: per mode)
     int nitems_cond = 0, nitems_lean = 0;// d_items = [conductor items | lean items]
     CUtensorMap tmA[EC3D_NVEC], tmU[EC3D_NVEC];   // per local vector: A part (4-D), dense U box (3-D)
     CUtensorMap tmPA[EC3D_NVEC], tmPU[EC3D_NVEC]; // same tensors with halo-free 64 x 8 boxes (L2 prefetch of r0 / b)
@@ -703,8 +715,10 @@ static void launch_tma_kind(ec3d_handle *h, cudaStream_t st, const TmaMaps &tm, 
 {
     if (nitems <= 0) return;
     Solver &s = h->sol;
+    // (the fused exchange applies to the solver's own launches; ec3d_apply_operator & co. use MODE_PLAIN)
     k_spmv_tma<MODE, NSTAGE, HAS_U, CPS><<<nitems, dim3(32, 8), tma_smem_bytes<MODE, HAS_U>(NSTAGE), st>>>(
-        tm, h->G, h->cf, h->mc0, items, vs, ctl, s.partials, s.pstride, pbase, expected);
+        tm, h->G, h->cf, h->mc0, items, vs, ctl, s.partials, s.pstride, pbase, expected, s.pt, s.cl,
+        (s.xfused && MODE != MODE_PLAIN) ? 1 : 0);
     g_launches.fetch_add(1);
 }
 
@@ -735,8 +749,11 @@ static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
             cudaEventRecord(h->ev_fork, h->st);
             cudaStreamWaitEvent(h->st2, h->ev_fork, 0);
         }
+        // conductor items: 1 CTA / SM (255 registers, no spills, deep ring) measures faster for MODE_SAS
+        // (0.856 vs 0.833 of the copy peak on plate(512)), 2 CTAs / SM for the single-input modes
+        const int ccps = h->ccps ? h->ccps : (MODE == MODE_SAS ? 1 : 2);
         if (h->nitems_cond) {
-            if (h->ccps == 1) launch_tma_kind<MODE, RingCfg<MODE>::COND1, true, 1>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
+            if (ccps == 1) launch_tma_kind<MODE, RingCfg<MODE>::COND1, true, 1>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
             else              launch_tma_kind<MODE, RingCfg<MODE>::COND2, true, 2>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
             ++nl;
         }
@@ -969,6 +986,7 @@ static int setup_p2p(ec3d_handle *h, bool want)
     cudaFree(d_x); cudaFree(d_flag);
     if (rc) return rc;
     h->p2p = all_ok;
+    pt.nU_send_lo = h->nU_send_lo; pt.nU_send_hi = h->nU_send_hi;
     if (!all_ok) {
         if (h->ipc_vecs_lo) cudaIpcCloseMemHandle(h->ipc_vecs_lo);
         if (h->ipc_vecs_hi) cudaIpcCloseMemHandle(h->ipc_vecs_hi);
@@ -1247,6 +1265,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     s.G = G; s.st = h->st;
     h->Uaf = h->vecs; h->Jaf = h->vecs + G.ltot;
     s.X = h->Uaf;
+    s.vecs_base = h->vecs; s.vstride = G.ltot;
     s.R = h->vecs + 2 * G.ltot; s.R0 = h->vecs + 3 * G.ltot; s.P = h->vecs + 4 * G.ltot; s.AP = h->vecs + 5 * G.ltot;
     s.S = h->vecs + 6 * G.ltot; s.AS = h->vecs + 7 * G.ltot;
     h->tmpx = h->vecs + 8 * G.ltot; h->tmpy = h->vecs + 9 * G.ltot;
@@ -1302,7 +1321,7 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         const char *ef = getenv("EC3D_TMA");
         h->tma = (sdx % 2 == 0) && !(ef && atoi(ef) == 0);
         const char *ec = getenv("EC3D_CCPS");
-        h->ccps = (ec && atoi(ec) == 1) ? 1 : 2;
+        h->ccps = (ec && (atoi(ec) == 1 || atoi(ec) == 2)) ? atoi(ec) : 0;      // 0: per mode
         const char *efu = getenv("EC3D_FUSE_S");
         s.fused_sas = h->tma && !(efu && atoi(efu) == 0);
     }
@@ -1329,13 +1348,19 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         }
         plan_spmv_items(G, zc, plane_major, items);
         h->zc = zc;
+        if (h->nranks > 1)
+            // several ranks: items far from the slab faces first, the ones that read halo planes (and wait
+            // for the neighbours' push, ec3d_comm.cuh) last -- by then the halo has long arrived
+            std::stable_sort(items.begin(), items.end(), [&](const WorkItem &a, const WorkItem &b) {
+                return std::min(a.kb - G.k0, G.k1 - a.ke) > std::min(b.kb - G.k0, G.k1 - b.ke);
+            });
         // two launches per SpMV: items with conductor cells, then lean items (each list keeps the planned order)
         std::stable_partition(items.begin(), items.end(), [](const WorkItem &w) { return w.has_u != 0; });
         h->nitems_cond = (int)std::count_if(items.begin(), items.end(), [](const WorkItem &w) { return w.has_u != 0; });
         h->nitems_lean = (int)items.size() - h->nitems_cond;
         if (getenv("EC3D_VERBOSE"))
             fprintf(stderr, "ec3d: TMA SpMV work list: zc = %d, %d conductor + %d lean items, %d CTA/SM for conductor items, "
-                            "s-update %s, BLAS-1 %s\n", zc, h->nitems_cond, h->nitems_lean, h->ccps,
+                            "s-update %s, BLAS-1 %s\n", zc, h->nitems_cond, h->nitems_lean, h->ccps ? h->ccps : 12,
                     s.fused_sas ? "fused into A*s" : "separate", s.ring ? "TMA ring" : "grid-stride");
         CUDA_TRY(cudaMalloc(&h->d_items, items.size() * sizeof(WorkItem)));
         CUDA_TRY(cudaMemcpy(h->d_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
@@ -1406,6 +1431,14 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
         int rc = setup_p2p(h, want);
         if (rc) return rc;
         s.p2p = h->p2p;
+        // exchanges fused into the compute kernels: needs peer memory, the TMA SpMV with the fused s-update
+        // and the TMA-ring BLAS-1 kernels (they carry the push / exchange code); EC3D_XFUSE=0 keeps the
+        // stand-alone exchange kernels between the compute kernels
+        const char *ex = getenv("EC3D_XFUSE");
+        s.xfused = h->p2p && h->tma && s.fused_sas && s.ring && !(ex && atoi(ex) == 0);
+        if (s.xfused) { s.pt = h->pt; s.cl = h->d_cl; }
+        if (getenv("EC3D_VERBOSE") && h->rank == 0)
+            fprintf(stderr, "ec3d: exchanges %s\n", s.xfused ? "fused into the compute kernels" : "as stand-alone launches");
     }
     // ---- iteration graph (single rank) ----
     {
@@ -1549,7 +1582,7 @@ extern "C" int ec3d_apply_operator(ec3d_handle *h, const double *x, double *y)
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = copy_in(h, h->tmpx, x);
     if (rc) return rc;
-    VecSet vs{h->tmpx, h->tmpy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    VecSet vs{h->tmpx, h->tmpy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
     const IterCtl ctl{h->sol.sc, h->sol.iter_base, 0};
     h->launches += h_spmv(h, MODE_PLAIN, vs, ctl);
     if ((rc = copy_out(h, y, h->tmpy))) return rc;

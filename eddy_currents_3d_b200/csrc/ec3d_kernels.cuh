@@ -15,6 +15,7 @@
 #pragma once
 #include "ec3d_async.cuh"
 #include "ec3d_common.cuh"
+#include "ec3d_comm.cuh"
 #include "ec3d_rows.cuh"
 
 #define DMUL(a, b) __dmul_rn((a), (b))
@@ -33,6 +34,7 @@ struct VecSet {
     double *R, *R0, *P;// MODE_INIT outputs
     const double *x2;  // MODE_SAS: Ap
     double *S;         // MODE_SAS: s output
+    int vi_y, vi_R, vi_P;   // fused halo push (several ranks): index of y / R / P among the handle's vectors
 };
 
 // --------------------------------------------------------------------------------------------
@@ -89,17 +91,66 @@ __device__ __forceinline__ dd block_sum(dd v, double *sh /* >= 64 doubles */)
     return r;
 }
 
+// Cross-rank part of a reduction, run by warp 0 of the last block (ec3d_comm.cuh): this rank's
+// double-double partials sh[0 .. 2*NRED) go to every rank's CommBlock, all contributions are awaited and
+// summed in rank order; the rounded sums land in sc->red[slot*].
+template <int NRED>
+__device__ __forceinline__ void xchg_reduce_warp(const PeerTable &pt, CommLocal *cl, Scal *sc, const double *sh,
+                                                 const int slot0, const int slot1, const int slot2)
+{
+    const int lane = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    unsigned long long e = 0;
+    if (lane == 0) { e = cl->red_epoch + 1ull; cl->red_epoch = e; }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    const int par = (int)(e & 1ull);
+    if (lane < pt.nranks) {
+        CommBlock *dst = pt.cb[lane];
+#pragma unroll
+        for (int q = 0; q < 2 * NRED; ++q) dst->red_val[par][pt.rank][q] = sh[q];
+        __threadfence_system();
+        st_release_sys(&dst->red_flag[pt.rank], e);
+    }
+    CommBlock *me = pt.cb[pt.rank];
+    bool ok = true;
+    if (lane < pt.nranks) ok = wait_epoch(&me->red_flag[lane], e);
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        if (!ok) cl->error = 1;
+        const int slots[3] = {slot0, slot1, slot2};
+#pragma unroll
+        for (int q = 0; q < NRED; ++q) {
+            dd t = dd_zero();                        // double-double sum in rank order, rounded once
+            for (int r = 0; r < pt.nranks; ++r)
+                dd_add_dd(t, dd{*(volatile double *)&me->red_val[par][r][2 * q], *(volatile double *)&me->red_val[par][r][2 * q + 1]});
+            sc->red[slots[q]] = dd_round(t);
+        }
+        __threadfence();
+    }
+}
+
+// Fused-exchange context of a kernel (several ranks over NVLink peer memory): pt == nullptr -> none.
+// raise = bit mask (1 << HALO_*) of the halo kinds this kernel has pushed to the neighbours.
+struct XchgCtx {
+    const PeerTable *pt;
+    CommLocal *cl;
+    int raise;
+};
+__device__ __forceinline__ XchgCtx no_xchg() { return XchgCtx{nullptr, nullptr, 0}; }
+
 // Stores this block's partial(s); the last block of the GROUP of kernels that share `sc->counter`
 // (expected = total number of blocks that will call this with the same partials array) sums all
-// partials and writes sc->red[slot0..2] (rounded; with several ranks the unrounded double-double
-// goes to red / red_lo and the cross-rank exchange rounds after summing the ranks).
+// partials and writes sc->red[slot0..2] (rounded).  Several ranks: with a fused-exchange context the
+// last block also raises the halo flags of the vectors this kernel pushed and does the cross-rank sum
+// itself; without one the unrounded double-double goes to red / red_lo for the exchange kernels.
 // partials: 2 * NRED * pstride doubles.
 template <int NRED>
 __device__ __forceinline__ void reduce_epilogue(dd a0, dd a1, dd a2, double *partials, int pstride, int pidx,
-                                                unsigned expected, Scal *sc, int slot0, int slot1, int slot2, double *sh)
+                                                unsigned expected, Scal *sc, int slot0, int slot1, int slot2, double *sh,
+                                                const XchgCtx xc = XchgCtx{nullptr, nullptr, 0})
 {
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     const int nthr = blockDim.x * blockDim.y * blockDim.z;
+    if (xc.pt) __threadfence_system();          // every thread: its stores into the neighbours' memory
     dd s0 = block_sum(a0, sh);
     dd s1 = dd_zero(), s2 = dd_zero();
     if (NRED > 1) s1 = block_sum(a1, sh);
@@ -109,12 +160,18 @@ __device__ __forceinline__ void reduce_epilogue(dd a0, dd a1, dd a2, double *par
         partials[2 * pidx] = s0.hi; partials[2 * pidx + 1] = s0.lo;
         if (NRED > 1) { partials[2 * (pstride + pidx)] = s1.hi; partials[2 * (pstride + pidx) + 1] = s1.lo; }
         if (NRED > 2) { partials[2 * (2 * pstride + pidx)] = s2.hi; partials[2 * (2 * pstride + pidx) + 1] = s2.lo; }
-        __threadfence();
+        if (xc.pt) __threadfence_system();      // this block's peer stores (fused halo push) before the ticket
+        else __threadfence();
         ticket_s = atomicAdd(&sc->counter, 1u);
     }
     __syncthreads();
     if (ticket_s != expected - 1) return;
     __threadfence();
+    if (xc.pt && xc.raise && tid == 0) {        // every block has fenced its stores: the halos are complete
+        __threadfence_system();
+        for (int k = 1; k < HALO_KINDS; ++k)
+            if (xc.raise & (1 << k)) halo_raise(*xc.pt, xc.cl, k);
+    }
     dd t0 = dd_zero(), t1 = dd_zero(), t2 = dd_zero();
     for (unsigned q = tid; q < expected; q += nthr) {
         dd_add_dd(t0, dd{__ldcg(partials + 2 * q), __ldcg(partials + 2 * q + 1)});
@@ -124,6 +181,16 @@ __device__ __forceinline__ void reduce_epilogue(dd a0, dd a1, dd a2, double *par
     t0 = block_sum(t0, sh);
     if (NRED > 1) t1 = block_sum(t1, sh);
     if (NRED > 2) t2 = block_sum(t2, sh);
+    if (xc.pt) {
+        __syncthreads();
+        if (tid == 0) {
+            sh[0] = t0.hi; sh[1] = t0.lo; sh[2] = t1.hi; sh[3] = t1.lo; sh[4] = t2.hi; sh[5] = t2.lo;
+            sc->counter = 0u;
+        }
+        __syncthreads();
+        if (tid < 32) xchg_reduce_warp<NRED>(*xc.pt, xc.cl, sc, sh, slot0, slot1, slot2);
+        return;
+    }
     if (tid == 0) {
         if (sc->multi) {
             sc->red[slot0] = t0.hi; sc->red_lo[slot0] = t0.lo;
@@ -595,14 +662,20 @@ struct ChunkMap {                                // chunks of the four owned seg
 #pragma unroll
         for (int s = 0; s < 4; ++s) cum[s + 1] = cum[s] + (G.own_len[s] + V1_CH - 1) / V1_CH;
     }
-    // local offset and length (doubles, even) of chunk c
-    __device__ __forceinline__ void locate(const SlabGeom &G, long long c, long long &loc, int &len) const
+    // local offset and length (doubles, even) of chunk c; seg / o = owned segment and offset inside it
+    __device__ __forceinline__ void locate(const SlabGeom &G, long long c, long long &loc, int &len, int &seg, long long &o) const
     {
         const int s = (int)(c >= cum[1]) + (int)(c >= cum[2]) + (int)(c >= cum[3]);
         const long long first = (s == 0) ? 0 : (s == 1) ? cum[1] : (s == 2) ? cum[2] : cum[3];   // (no dynamic indexing: registers)
-        const long long o = (c - first) * V1_CH;
+        o = (c - first) * V1_CH;
+        seg = s;
         loc = G.own_off[s] + o;
         len = (int)min((long long)V1_CH, G.own_len[s] - o);
+    }
+    __device__ __forceinline__ void locate(const SlabGeom &G, long long c, long long &loc, int &len) const
+    {
+        int seg; long long o;
+        locate(G, c, loc, len, seg, o);
     }
 };
 
@@ -675,7 +748,8 @@ __device__ __forceinline__ unsigned char *align128(unsigned char *p)
 __global__ void __launch_bounds__(256, 1)
 k_xr_update_tma(const SlabGeom G, double *__restrict__ X, const double *__restrict__ P, const double *__restrict__ S,
                 const double *__restrict__ AS, double *__restrict__ R, const double *__restrict__ R0, const IterCtl ctl,
-                double *partials, const int pstride, const unsigned expected)
+                double *partials, const int pstride, const unsigned expected,
+                const __grid_constant__ PeerTable pt, CommLocal *cl, const int xf, const int vi_R)
 {
     extern __shared__ unsigned char smem_raw[];
     __shared__ double sh[64];
@@ -705,8 +779,8 @@ k_xr_update_tma(const SlabGeom G, double *__restrict__ X, const double *__restri
     dd a0 = dd_zero(), a1 = dd_zero();
     for (long long i = 0; i < ring.mine; ++i) {
         const double *st = ring.acquire(i);
-        long long loc; int len;
-        ring.cm.locate(G, ring.c0 + i * ring.cs, loc, len);
+        long long loc, o0; int len, seg;
+        ring.cm.locate(G, ring.c0 + i * ring.cs, loc, len, seg, o0);
         double2 x[2], p[2], s[2], as[2], r0[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -728,18 +802,34 @@ k_xr_update_tma(const SlabGeom G, double *__restrict__ X, const double *__restri
                 r.y = DSUB(s[u].y, DMUL(omega, as[u].y));
                 st2(X + loc + e, x[u].x, x[u].y);
                 st2(R + loc + e, r.x, r.y);
+                if (xf) peer_push2(pt, G, vi_R, seg, o0 + e, r.x, r.y);      // R is an input of the next A*s SpMV
                 dd_add_d(a0, __fma_rn(r.y, r.y, DMUL(r.x, r.x)));
                 dd_add_d(a1, __fma_rn(r.y, r0[u].y, DMUL(r.x, r0[u].x)));
             }
         }
     }
-    reduce_epilogue<2>(a0, a1, dd_zero(), partials, pstride, blockIdx.x, expected, sc, RED_RR, RED_RR0N, RED_RR0N, sh);
+    reduce_epilogue<2>(a0, a1, dd_zero(), partials, pstride, blockIdx.x, expected, sc, RED_RR, RED_RR0N, RED_RR0N, sh,
+                       xf ? XchgCtx{&pt, cl, 1 << HALO_R} : no_xchg());
 }
 
 // K6 (TMA ring): exit tests, beta, P = R + beta*(P - omega*AP), restart.     solvers.f90:34-49
+// all blocks of the p-update have fenced their peer stores: the last one tells the neighbours
+__device__ __forceinline__ void p_push_done(const PeerTable &pt, CommLocal *cl)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    if (atomicAdd(&cl->ticket_p, 1u) != gridDim.x - 1) return;
+    cl->ticket_p = 0u;
+    __threadfence_system();
+    halo_raise(pt, cl, HALO_P);
+}
+
 __global__ void __launch_bounds__(256, 2)
 k_p_update_tma(const SlabGeom G, double *__restrict__ P, const double *__restrict__ R, const double *__restrict__ AP,
-               double *__restrict__ R0, const IterCtl ctl)
+               double *__restrict__ R0, const IterCtl ctl,
+               const __grid_constant__ PeerTable pt, CommLocal *cl, const int xf, const int vi_P)
 {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full[P_NST], empty[P_NST];
@@ -769,14 +859,16 @@ k_p_update_tma(const SlabGeom G, double *__restrict__ P, const double *__restric
     if (restart) {                                                      // R0 = R; P = R   (rare: plain loads)
         ChunkMap cm; cm.init(G);
         for (long long c = blockIdx.x; c < cm.cum[4]; c += gridDim.x) {
-            long long loc; int len;
-            cm.locate(G, c, loc, len);
+            long long loc, o0; int len, seg;
+            cm.locate(G, c, loc, len, seg, o0);
             for (int e = 2 * tid; e < len; e += 512) {
                 const double2 r = ld2(R + loc + e);
                 st2(R0 + loc + e, r.x, r.y);
                 st2(P + loc + e, r.x, r.y);
+                if (xf) peer_push2(pt, G, vi_P, seg, o0 + e, r.x, r.y);
             }
         }
+        if (xf) p_push_done(pt, cl);
         return;
     }
     BulkRing<3, P_NST> ring;
@@ -784,8 +876,8 @@ k_p_update_tma(const SlabGeom G, double *__restrict__ P, const double *__restric
     ring.start(G, align128(smem_raw), full, empty);
     for (long long i = 0; i < ring.mine; ++i) {
         const double *st = ring.acquire(i);
-        long long loc; int len;
-        ring.cm.locate(G, ring.c0 + i * ring.cs, loc, len);
+        long long loc, o0; int len, seg;
+        ring.cm.locate(G, ring.c0 + i * ring.cs, loc, len, seg, o0);
         double2 r[2], p[2], ap[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -796,11 +888,15 @@ k_p_update_tma(const SlabGeom G, double *__restrict__ P, const double *__restric
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int e = 2 * (tid + u * 256);
-            if (e < len)
-                st2(P + loc + e, DADD(r[u].x, DMUL(beta, DSUB(p[u].x, DMUL(omega, ap[u].x)))),
-                    DADD(r[u].y, DMUL(beta, DSUB(p[u].y, DMUL(omega, ap[u].y)))));
+            if (e < len) {
+                const double px = DADD(r[u].x, DMUL(beta, DSUB(p[u].x, DMUL(omega, ap[u].x))));
+                const double py = DADD(r[u].y, DMUL(beta, DSUB(p[u].y, DMUL(omega, ap[u].y))));
+                st2(P + loc + e, px, py);
+                if (xf) peer_push2(pt, G, vi_P, seg, o0 + e, px, py);        // P is the input of the next A*p SpMV
+            }
         }
     }
+    if (xf) p_push_done(pt, cl);
 }
 
 // K3 (TMA ring; CSR drop-in path, where the SpMV is not the fused MODE_SAS kernel):

@@ -1,75 +1,22 @@
-// ec3d_p2p.cuh -- halo exchange and scalar all-reduce over NVLink peer memory (one process per GPU).
+// ec3d_p2p.cuh -- stand-alone exchange kernels over NVLink peer memory (one process per GPU).
 //
-// The BiCGSTABwr iteration has two nearest-neighbour exchanges (one plane of Ax, Ay, Az and two
-// planes of the dense U box per neighbour, before each SpMV) and four reductions of 1-2 doubles.
-// Both are latency, not bandwidth, problems, so they are done by small kernels of this library
-// that store straight into the neighbour's memory (CUDA IPC mappings of every rank's vector
-// allocation and of a small CommBlock) and signal with monotonically increasing epochs:
+// Inside the BiCGSTABwr iteration the exchanges are FUSED into the compute kernels (ec3d_comm.cuh: halo
+// planes are pushed by the kernel that produces a vector, reductions are finished across ranks by the
+// last block of the kernel that computes them).  The kernels here serve everything outside that loop --
+// the halo of the initial guess / of Uaf before the right-hand side, ec3d_apply_operator, the output
+// fields, barriers -- and the un-fused fallback sequence (odd grids, EC3D_XFUSE=0):
 //
-//   k_halo_push   copies the boundary planes of one vector into the neighbours' halo slots, every
-//                 block fences (system scope), the last block raises the neighbours' halo flag
+//   k_halo_push   copies the boundary planes of one or two vectors into the neighbours' halo slots, every
+//                 block fences (system scope), the last block raises the neighbours' HALO_GEN flag
 //   k_halo_wait   one thread waits until both neighbours' flags reached this rank's epoch
 //   k_reduce_xchg stores this rank's partial result(s) into every rank's CommBlock (slot chosen by
-//                 epoch parity), raises the flags, waits for all contributions and sums them in
-//                 rank order in double-double -- bit-identical on every rank (all ranks take the
-//                 same branches) and, rounded, the same value a single GPU computes
-//
-// All epochs live in device memory and are advanced by the kernels themselves, so a whole chunk
-// of iterations (compute + exchange) is one CUDA graph.  Two pushes into the same halo slot are
-// always separated by a reduction the reader takes part in after its SpMV, and a reduction slot is
-// reused only two epochs later, so there are no write-after-read hazards.  Waits give up after
-// ~30 s and set CommLocal::error instead of hanging the GPU.
+//                 epoch parity), raises the flags, waits for all contributions and sums them in rank
+//                 order in double-double -- bit-identical on every rank and, rounded, the same value a
+//                 single GPU computes
 #pragma once
 #include "ec3d_common.cuh"
+#include "ec3d_comm.cuh"
 #include "ec3d_kernels.cuh"
-
-#define EC3D_MAX_RANKS 16
-
-struct CommBlock {                                   // written by peers
-    unsigned long long halo_flag[2];                 // [0] from rank-1, [1] from rank+1: epoch of their last push
-    unsigned long long red_flag[EC3D_MAX_RANKS];     // epoch of rank r's last contribution
-    double red_val[2][EC3D_MAX_RANKS][8];            // [epoch parity][rank][hi0, lo0, hi1, lo1, hi2, lo2, -, -]
-};
-
-struct CommLocal {                                   // this rank only
-    unsigned long long halo_epoch, red_epoch;
-    unsigned int ticket;
-    int error;                                       // 1: a wait timed out
-};
-
-struct PeerGeom {                                    // what a rank needs to know about a neighbour's layout
-    long long segA, offU, nUlo, nUown, ltot;
-    int nzl, pad;
-};
-
-struct PeerTable {
-    int nranks, rank;
-    CommBlock *cb[EC3D_MAX_RANKS];                   // every rank's CommBlock (own: local pointer)
-    double *vecs_lo, *vecs_hi;                       // vector allocations of rank-1 / rank+1 (or null)
-    PeerGeom g_lo, g_hi;
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// spins until *p >= want; false on timeout
-__device__ __forceinline__ bool wait_epoch(const unsigned long long *p, unsigned long long want)
-{
-    const long long t0 = clock64();
-    while (ld_acquire_sys(p) < want) {
-        if (clock64() - t0 > 60000000000LL) return false;      // ~30 s: ranks may be skewed by host work
-        __nanosleep(64);
-    }
-    return true;
-}
 
 // Copies this rank's boundary planes of local vector `vidx` (and `vidx2` when >= 0) into the neighbours'
 // halo slots.  Work units are 16-byte pairs; per vector up to 8 segments: 3 A planes + U planes towards each side.
@@ -117,23 +64,15 @@ k_halo_push(const SlabGeom G, const PeerTable pt, double *__restrict__ vecs, con
     __syncthreads();
     if (!last || threadIdx.x != 0) return;
     __threadfence_system();
-    const unsigned long long e = cl->halo_epoch + 1ull;
-    cl->halo_epoch = e;
     cl->ticket = 0u;
-    if (pt.rank > 0) st_release_sys(&pt.cb[pt.rank - 1]->halo_flag[1], e);            // I am its upper neighbour
-    if (pt.rank < pt.nranks - 1) st_release_sys(&pt.cb[pt.rank + 1]->halo_flag[0], e);  // I am its lower neighbour
+    halo_raise(pt, cl, HALO_GEN);
 }
 
 __global__ void k_halo_wait(const PeerTable pt, const Scal *sc, const int check_done, CommLocal *cl)
 {
     if (threadIdx.x != 0) return;
     if (check_done && sc->done) return;
-    const unsigned long long e = cl->halo_epoch;       // already advanced by this rank's own push
-    CommBlock *me = pt.cb[pt.rank];
-    bool ok = true;
-    if (pt.rank > 0) ok = wait_epoch(&me->halo_flag[0], e) && ok;
-    if (pt.rank < pt.nranks - 1) ok = wait_epoch(&me->halo_flag[1], e) && ok;
-    if (!ok) cl->error = 1;
+    halo_wait(pt, cl, HALO_GEN, true, true);           // epoch already advanced by this rank's own push
     __threadfence_system();
 }
 

@@ -140,10 +140,28 @@ __global__ void k_build_cls2(const SlabGeom G, const int *__restrict__ geo, cons
 // dots are accumulated with fma (the reference's sequential dot_product order is not reproducible
 // in parallel anyway; fewer roundings, half the FP64 instructions).  xa, xb = the SpMV input at the
 // two cells (MODE_SAS: s = r - alpha*Ap, which this kernel also materialises in vs.S).
+// Several ranks (px.on): rows of a slab-boundary plane that are inputs of a later SpMV (Ap; R and P of the
+// initial residual) are also stored into the neighbour's halo slot (ec3d_comm.cuh) -- seg / o = owned
+// segment and offset of the pair inside it.
+struct PushCtx {
+    const PeerTable *pt;
+    const SlabGeom *G;
+    bool on;                // this plane is a boundary plane of the slab (block uniform)
+};
+__device__ __forceinline__ void push_rows(const PushCtx &px, const int vi, const int seg, const long long o, const double a,
+                                          const double b, const bool wa, const bool wb)
+{
+    if (wa && wb) peer_push2(*px.pt, *px.G, vi, seg, o, a, b);
+    else {
+        if (wa) peer_push1(*px.pt, *px.G, vi, seg, o, a);
+        if (wb) peer_push1(*px.pt, *px.G, vi, seg, o + 1, b);
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void pair_out(const double ya, const double yb, const bool wa, const bool wb, const long long idx,
                                          const double xa, const double xb, const double2 aux, const VecSet &vs,
-                                         double &a0, double &a1, double &a2)
+                                         double &a0, double &a1, double &a2, const PushCtx &px, const int seg, const long long o)
 {
     if (MODE == MODE_INIT) {
         const double ra = DSUB(aux.x, ya), rb = DSUB(aux.y, yb);
@@ -152,6 +170,7 @@ __device__ __forceinline__ void pair_out(const double ya, const double yb, const
             if (wa) { vs.R[idx] = ra; vs.R0[idx] = ra; vs.P[idx] = ra; }
             if (wb) { vs.R[idx + 1] = rb; vs.R0[idx + 1] = rb; vs.P[idx + 1] = rb; }
         }
+        if (px.on) { push_rows(px, vs.vi_R, seg, o, ra, rb, wa, wb); push_rows(px, vs.vi_P, seg, o, ra, rb, wa, wb); }
         if (wa) { a0 = __fma_rn(aux.x, aux.x, a0); a1 = __fma_rn(ra, ra, a1); }
         if (wb) { a0 = __fma_rn(aux.y, aux.y, a0); a1 = __fma_rn(rb, rb, a1); }
         return;
@@ -163,6 +182,7 @@ __device__ __forceinline__ void pair_out(const double ya, const double yb, const
         if (wa) { vs.y[idx] = ya; if (MODE == MODE_SAS) vs.S[idx] = xa; }
         if (wb) { vs.y[idx + 1] = yb; if (MODE == MODE_SAS) vs.S[idx + 1] = xb; }
     }
+    if (MODE == MODE_AP && px.on) push_rows(px, vs.vi_y, seg, o, ya, yb, wa, wb);
     if (MODE == MODE_AP) {
         if (wa) a0 = __fma_rn(ya, aux.x, a0);
         if (wb) a0 = __fma_rn(yb, aux.y, a0);
@@ -253,7 +273,8 @@ __device__ __forceinline__ double2 in2(const double *p, const int d2, const doub
 template <int MODE, int NSTAGE, bool HAS_U>
 __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom &G, const Coef &cf, const MatCoef &mc,
                                                const VecSet &vs, const TmaCtx &t, unsigned char *smem,
-                                               unsigned long long *full, unsigned *cnt, dd &acc0, dd &acc1, dd &acc2)
+                                               unsigned long long *full, unsigned *cnt, dd &acc0, dd &acc1, dd &acc2,
+                                               const PeerTable *pt, const bool xf)
 {
     using namespace tma;
     using ST = Stage<MODE, HAS_U>;
@@ -354,6 +375,11 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                 // this thread's dot-product terms of plane k: summed in a fixed order here, accumulated
                 // across planes in double-double (independent of how z is cut into items and slabs)
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                // fused halo push: planes k0 / k1-1 (A rows) and the two planes nearest each slab face (U rows)
+                const bool pushes = xf && (MODE == MODE_AP || MODE == MODE_INIT);
+                const PushCtx pxA{pt, &G, pushes && (k == G.k0 || k == G.k1 - 1)};
+                const PushCtx pxU{pt, &G, pushes && (k < G.k0 + 2 || k >= G.k1 - 2)};
+                const long long oA = pA - kdz, oU = pU - G.own_off[3];       // offsets inside the owned segments
                 own_pair(sz_, q);
                 if (t.active) {
                     const unsigned char *stp = smem + sprev * ST::BYTES;
@@ -377,7 +403,7 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                             const double xm = in1<SAS>(tt - 1, A2, alpha), xp = in1<SAS>(tt + 2, A2, alpha);
                             const double ya = row7(czm, t.cym, cf.msx, dgA, t.cxpA, t.cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
                             const double yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
-                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2, pxA, a, oA);
                         }
                     } else if (ca == 0x40 && cb == 0x40) {
                         // ---- both cells are interior conductor cells (all six neighbours conductor):
@@ -411,7 +437,7 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                             const double apB = (a == 0) ? xp : (a == 1) ? yp.y : z1[a].y;
                             suA = DADD(suA, DMUL(cf.ua_p[a], amA)); suA = DADD(suA, DMUL(cf.ua_m[a], apA));
                             suB = DADD(suB, DMUL(cf.ua_p[a], amB)); suB = DADD(suB, DMUL(cf.ua_m[a], apB));
-                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2, pxA, a, oA);
                         }
                         // U columns k-1, j-1, i-1, centre, i+1, j+1, k+1
                         suA = DADD(suA, DMUL(cf.msz, ugm.x)); suB = DADD(suB, DMUL(cf.msz, ugm.y));
@@ -421,7 +447,7 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                         suA = DADD(suA, DMUL(cf.msx, ugc.y)); suB = DADD(suB, DMUL(cf.msx, uxp));
                         suA = DADD(suA, DMUL(cf.msy, uyp.x)); suB = DADD(suB, DMUL(cf.msy, uyp.y));
                         suA = DADD(suA, DMUL(cf.msz, ugp.x)); suB = DADD(suB, DMUL(cf.msz, ugp.y));
-                        pair_out<MODE>(suA, suB, true, true, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2);
+                        pair_out<MODE>(suA, suB, true, true, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2, pxU, 3, oU);
                     } else {
                         // ---- conductor-surface cells / mixed pairs (never on a domain face): generic per-cell rows ----
                         const double2 ugm = ug3[sm_], ugc = ug3[sc_], ugp = ug3[sz_];
@@ -480,13 +506,13 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                             } else {
                                 yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
                             }
-                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2, pxA, a, oA);
                         }
                         // U rows
                         double sa_ = 0.0, sb_ = 0.0;
                         if (ca) sa_ = urow_u(cf, ca, ua[2].m1, ua[1].m1, ua[0].m1, ugc.x, ua[0].p1, ua[1].p1, ua[2].p1, suA);
                         if (cb) sb_ = urow_u(cf, cb, ub[2].m1, ub[1].m1, ub[0].m1, ugc.y, ub[0].p1, ub[1].p1, ub[2].p1, suB);
-                        pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2);
+                        pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2, pxU, 3, oU);
                     }
                 }
                 if (MODE != MODE_PLAIN) {
@@ -510,7 +536,7 @@ template <int MODE, int NSTAGE, bool HAS_U, int CPS>
 __global__ void __launch_bounds__(256, CPS)
 k_spmv_tma(const __grid_constant__ TmaMaps tm, const SlabGeom G, const Coef cf, const MatCoef mc,
            const WorkItem *__restrict__ items, const VecSet vs, const IterCtl ctl, double *partials, const int pstride,
-           const int pbase, const unsigned expected)
+           const int pbase, const unsigned expected, const __grid_constant__ PeerTable pt, CommLocal *cl, const int xf)
 {
     using namespace tma;
     extern __shared__ unsigned char smem_raw[];
@@ -551,22 +577,35 @@ k_spmv_tma(const __grid_constant__ TmaMaps tm, const SlabGeom G, const Coef cf, 
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); cnt[s] = 0u; }
         fence_barrier_init();
         fence_proxy_async();
+        if (xf && (MODE == MODE_AP || MODE == MODE_SAS)) {
+            // only the items that read halo planes (A: kb-1 / ke; U: two planes) wait for the neighbours'
+            // fused push of this kernel's input vector(s); everything else starts right away
+            const bool lo = w.kb < G.k0 + 2, hi = w.ke > G.k1 - 2;
+            if (lo || hi) {
+                if (MODE == MODE_AP) halo_wait(pt, cl, HALO_P, lo, hi);
+                else { halo_wait(pt, cl, HALO_R, lo, hi); halo_wait(pt, cl, HALO_AP, lo, hi); }
+                asm volatile("fence.proxy.async;" ::: "memory");   // peer-written halo data -> the TMA (async proxy) reads below
+            }
+        }
     }
     __syncthreads();
 
     dd a0 = dd_zero(), a1 = dd_zero(), a2 = dd_zero();
-    tma_plane_loop<MODE, NSTAGE, HAS_U>(tm, G, cf, mc, vs, t, smem, full, cnt, a0, a1, a2);
+    tma_plane_loop<MODE, NSTAGE, HAS_U>(tm, G, cf, mc, vs, t, smem, full, cnt, a0, a1, a2, &pt, xf != 0);
 
     if (MODE != MODE_PLAIN) {
         const int pidx = pbase + blockIdx.x;
         if (MODE == MODE_AP)
-            reduce_epilogue<1>(a0, dd_zero(), dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_APR0, RED_APR0, RED_APR0, sh);
+            reduce_epilogue<1>(a0, dd_zero(), dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_APR0, RED_APR0, RED_APR0, sh,
+                               xf ? XchgCtx{&pt, cl, 1 << HALO_AP} : no_xchg());
         else if (MODE == MODE_AS)
             reduce_epilogue<2>(a0, a1, dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, RED_ASAS, sh);
         else if (MODE == MODE_SAS)
-            reduce_epilogue<3>(a0, a1, a2, partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, RED_SS, sh);
+            reduce_epilogue<3>(a0, a1, a2, partials, pstride, pidx, expected, ctl.sc, RED_ASS, RED_ASAS, RED_SS, sh,
+                               xf ? XchgCtx{&pt, cl, 0} : no_xchg());
         else
-            reduce_epilogue<2>(a0, a1, dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_BB, RED_RR_INIT, RED_RR_INIT, sh);
+            reduce_epilogue<2>(a0, a1, dd_zero(), partials, pstride, pidx, expected, ctl.sc, RED_BB, RED_RR_INIT, RED_RR_INIT, sh,
+                               xf ? XchgCtx{&pt, cl, (1 << HALO_P) | (1 << HALO_R)} : no_xchg());
     }
 }
 
