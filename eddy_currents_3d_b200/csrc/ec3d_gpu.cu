@@ -578,6 +578,7 @@ struct ec3d_handle {
     int mat0 = 0;
     MatCoef mc0{};
     bool tma = false;                    // k_spmv_tma usable (even sdx); else k_air_spmv + k_cond_spmv
+    int jacobi = 0;                      // optional Jacobi scaling of the solver's operator (ec3d_set_preconditioner)
     int ccps = 0;                        // CTAs per SM of the conductor-item kernel (EC3D_CCPS = 1 | 2; 0: per mode)
     int nitems_cond = 0, nitems_lean = 0;// d_items = [conductor items | lean items]
     CUtensorMap tmA[EC3D_NVEC], tmU[EC3D_NVEC];   // per local vector: A part (4-D), dense U box (3-D)
@@ -709,14 +710,14 @@ template <int MODE> struct RingCfg {
     static constexpr int COND1 = (MODE == MODE_SAS) ? 4 : (MODE == MODE_PLAIN) ? 8 : 6;
 };
 
-template <int MODE, int NSTAGE, bool HAS_U, int CPS>
+template <int MODE, int NSTAGE, bool HAS_U, int CPS, bool JAC>
 static void launch_tma_kind(ec3d_handle *h, cudaStream_t st, const TmaMaps &tm, const WorkItem *items, int nitems, int pbase,
                             unsigned expected, const VecSet &vs, const IterCtl &ctl)
 {
     if (nitems <= 0) return;
     Solver &s = h->sol;
     // (the fused exchange applies to the solver's own launches; ec3d_apply_operator & co. use MODE_PLAIN)
-    k_spmv_tma<MODE, NSTAGE, HAS_U, CPS><<<nitems, dim3(32, 8), tma_smem_bytes<MODE, HAS_U>(NSTAGE), st>>>(
+    k_spmv_tma<MODE, NSTAGE, HAS_U, CPS, JAC><<<nitems, dim3(32, 8), tma_smem_bytes<MODE, HAS_U>(NSTAGE), st>>>(
         tm, h->G, h->cf, h->mc0, items, vs, ctl, s.partials, s.pstride, pbase, expected, s.pt, s.cl,
         (s.xfused && MODE != MODE_PLAIN) ? 1 : 0);
     g_launches.fetch_add(1);
@@ -751,14 +752,18 @@ static int launch_stencil(ec3d_handle *h, const VecSet &vs, const IterCtl &ctl)
         }
         // conductor items: 1 CTA / SM (255 registers, no spills, deep ring) measures faster for MODE_SAS
         // (0.856 vs 0.833 of the copy peak on plate(512)), 2 CTAs / SM for the single-input modes
-        const int ccps = h->ccps ? h->ccps : (MODE == MODE_SAS ? 1 : 2);
+        // (the optional Jacobi scaling is a separate instantiation so that the default kernels carry none of it)
+        const bool jac = h->jacobi && MODE != MODE_PLAIN;
+        const int ccps = jac ? 1 : h->ccps ? h->ccps : (MODE == MODE_SAS ? 1 : 2);
         if (h->nitems_cond) {
-            if (ccps == 1) launch_tma_kind<MODE, RingCfg<MODE>::COND1, true, 1>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
-            else              launch_tma_kind<MODE, RingCfg<MODE>::COND2, true, 2>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
+            if (jac)            launch_tma_kind<MODE, RingCfg<MODE>::COND1, true, 1, true>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
+            else if (ccps == 1) launch_tma_kind<MODE, RingCfg<MODE>::COND1, true, 1, false>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
+            else                launch_tma_kind<MODE, RingCfg<MODE>::COND2, true, 2, false>(h, h->st, tm, h->d_items, h->nitems_cond, 0, expected, vs, ctl);
             ++nl;
         }
         if (h->nitems_lean) {
-            launch_tma_kind<MODE, RingCfg<MODE>::LEAN, false, 2>(h, stl, tm, h->d_items + h->nitems_cond, h->nitems_lean, h->nitems_cond, expected, vs, ctl);
+            if (jac) launch_tma_kind<MODE, RingCfg<MODE>::LEAN, false, 2, true>(h, stl, tm, h->d_items + h->nitems_cond, h->nitems_lean, h->nitems_cond, expected, vs, ctl);
+            else     launch_tma_kind<MODE, RingCfg<MODE>::LEAN, false, 2, false>(h, stl, tm, h->d_items + h->nitems_cond, h->nitems_lean, h->nitems_cond, expected, vs, ctl);
             ++nl;
         }
         if (fork) {
@@ -883,13 +888,49 @@ static void plan_spmv_items(const SlabGeom &G, int zc, bool plane_major, std::ve
         std::stable_sort(items.begin(), items.end(), [](const WorkItem &a, const WorkItem &b) { return a.kb < b.kb; });
 }
 
-// Planes per item: measured on plate(256) / plate(512), 32..48 is the flat optimum (longer items
-// leave too few CTAs for the last round, shorter ones pay the 2 extra planes and the pipeline fill
-// more often); small grids get shorter items so that every SM has work.
+// Planes per item.  Long items amortise the 2 halo planes and the pipeline fill, short ones fill the
+// last wave of CTAs evenly; which wins depends on how many (tile column x z) items the slab has relative
+// to the 2 x 148 resident CTAs.  So the host SIMULATES the launch for a few candidate lengths -- list
+// scheduling of the planned items (conductor items first, about 2.2x the cost per plane, measured) on
+// 296 CTA slots -- and keeps the length with the best useful-work / (slots x makespan).  On plate(512)
+// every candidate is within 2 %; on plate(256) and on the 64-plane slabs of an 8-GPU run the spread is
+// 0.84 ... 0.98 (scripts: see DESIGN.md section 3.1).
+static double simulate_items(const std::vector<WorkItem> &items)
+{
+    const int slots = 2 * 148;
+    std::vector<double> heap(slots, 0.0);               // min-heap of slot finish times
+    auto cmp = [](double a, double b) { return a > b; };
+    double useful = 0.0;
+    auto run = [&](bool cond) {
+        for (const WorkItem &w : items) {
+            if ((w.has_u != 0) != cond) continue;
+            const double per = w.has_u ? 2.2 : 1.0;
+            const int nz = w.ke - w.kb;
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            heap.back() += per * (nz + 2.0);            // ~1 plane for the 2 halo planes (loads only) + ~1 of pipeline fill
+            std::push_heap(heap.begin(), heap.end(), cmp);
+            useful += per * nz;
+        }
+    };
+    run(true); run(false);
+    const double makespan = *std::max_element(heap.begin(), heap.end());
+    return makespan > 0.0 ? useful / (slots * makespan) : 0.0;
+}
+
 static int default_item_planes(const SlabGeom &G)
 {
-    const int tx = (G.sdx + tma::TX - 1) / tma::TX, ty = (G.sdy + tma::TY - 1) / tma::TY;
-    return (int)std::min<long long>(48, std::max<long long>(4, (long long)G.nzl * tx * ty / (2 * 148)));
+    static const int cand[] = {12, 16, 20, 24, 28, 32, 40, 48, 64};
+    int best = 48;
+    double best_eff = -1.0;
+    std::vector<WorkItem> items;
+    for (int zc : cand) {
+        if (zc > std::max(4, G.nzl)) continue;
+        plan_spmv_items(G, zc, true, items);
+        const double e = simulate_items(items);
+        if (e > best_eff + 1e-9) { best_eff = e; best = zc; }
+    }
+    if (best_eff < 0.0) best = std::max(2, std::min(48, G.nzl));
+    return best;
 }
 
 extern "C" int ec3d_plan_spmv_items(int32_t sdx, int32_t sdy, int32_t k0, int32_t k1, const int32_t box[6], int32_t zc,
@@ -1070,11 +1111,16 @@ static cudaError_t set_attr_mode()
 {
     cudaError_t e;
     using RC = RingCfg<MODE>;
-    if ((e = cudaFuncSetAttribute(k_spmv_tma<MODE, RC::LEAN, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if ((e = cudaFuncSetAttribute(k_spmv_tma<MODE, RC::LEAN, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   tma_smem_bytes<MODE, false>(RC::LEAN))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_spmv_tma<MODE, RC::COND2, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if ((e = cudaFuncSetAttribute(k_spmv_tma<MODE, RC::COND2, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   tma_smem_bytes<MODE, true>(RC::COND2))) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_spmv_tma<MODE, RC::COND1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if ((e = cudaFuncSetAttribute(k_spmv_tma<MODE, RC::COND1, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tma_smem_bytes<MODE, true>(RC::COND1))) != cudaSuccess) return e;
+    if (MODE == MODE_PLAIN) return cudaSuccess;
+    if ((e = cudaFuncSetAttribute(k_spmv_tma<MODE, RC::LEAN, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tma_smem_bytes<MODE, false>(RC::LEAN))) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_spmv_tma<MODE, RC::COND1, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 tma_smem_bytes<MODE, true>(RC::COND1));
 }
 static int set_tma_smem_attr()
@@ -1463,6 +1509,28 @@ extern "C" int ec3d_create(const ec3d_config *cfg, ec3d_handle **out)
         return rc;
     }
     *out = h;
+    return EC3D_OK;
+}
+
+// optional Jacobi (diagonal) preconditioning, OFF by default because it changes the iterates
+// and with them iteration-count parity with the reference.  kind = 1: the solver works on D^-1 A x = D^-1 b
+// (every row and the right-hand side scaled by 1/diagonal: 2(sx+sy+sz) [+ 2C/dt in the conductor],
+// EC3D.f90:651,663; the face diagonals of :533-642); the stopping test then measures the scaled residual.
+extern "C" int ec3d_set_preconditioner(ec3d_handle *h, int32_t kind)
+{
+    if (!h || (kind != 0 && kind != 1)) { ec3d_set_error("preconditioner kind must be 0 (none) or 1 (Jacobi)"); return EC3D_ERR_ARG; }
+    if (kind == 1 && !h->tma) { ec3d_set_error("the Jacobi option needs the TMA SpMV (even sdx)"); return EC3D_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    if (h->jacobi == kind) return EC3D_OK;
+    h->jacobi = kind;
+    Solver &s = h->sol;
+    if (s.graph) {                                   // the captured launches carry the old flag
+        cudaGraphExecDestroy(s.graph);
+        s.graph = nullptr;
+        int rc = solver_build_graph(s, 8);
+        if (rc) return rc;
+    }
     return EC3D_OK;
 }
 

@@ -158,11 +158,18 @@ __device__ __forceinline__ void push_rows(const PushCtx &px, const int vi, const
     }
 }
 
+// ja / jb: optional Jacobi scaling (ec3d_set_preconditioner, OFF by default): the rows of D^-1 A, i.e.
+// every row result -- and the right-hand side in MODE_INIT -- times 1/diagonal; 0.0 = off (exact reference rows).
 template <int MODE>
-__device__ __forceinline__ void pair_out(const double ya, const double yb, const bool wa, const bool wb, const long long idx,
-                                         const double xa, const double xb, const double2 aux, const VecSet &vs,
-                                         double &a0, double &a1, double &a2, const PushCtx &px, const int seg, const long long o)
+__device__ __forceinline__ void pair_out(double ya, double yb, const bool wa, const bool wb, const long long idx,
+                                         const double xa, const double xb, double2 aux, const VecSet &vs,
+                                         double &a0, double &a1, double &a2, const PushCtx &px, const int seg, const long long o,
+                                         const double ja = 0.0, const double jb = 0.0)
 {
+    if (ja != 0.0) {
+        ya = DMUL(ja, ya); yb = DMUL(jb, yb);
+        if (MODE == MODE_INIT) { aux.x = DMUL(ja, aux.x); aux.y = DMUL(jb, aux.y); }
+    }
     if (MODE == MODE_INIT) {
         const double ra = DSUB(aux.x, ya), rb = DSUB(aux.y, yb);
         if (wa && wb) { st2(vs.R + idx, ra, rb); st2(vs.R0 + idx, ra, rb); st2(vs.P + idx, ra, rb); }
@@ -270,7 +277,7 @@ __device__ __forceinline__ double2 in2(const double *p, const int d2, const doub
 }
 
 // Plane loop of one work item.  HAS_U = item contains conductor cells.
-template <int MODE, int NSTAGE, bool HAS_U>
+template <int MODE, int NSTAGE, bool HAS_U, bool JAC>
 __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom &G, const Coef &cf, const MatCoef &mc,
                                                const VecSet &vs, const TmaCtx &t, unsigned char *smem,
                                                unsigned long long *full, unsigned *cnt, dd &acc0, dd &acc1, dd &acc2,
@@ -387,6 +394,10 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                     const bool zl = (k == 0), zh = (k == sdz - 1);
                     const double czm = zh ? cf.bhi[2] : cf.msz, czp = zl ? cf.blo[2] : cf.msz;
                     const double dgA = (zl | zh) ? t.dgA1 : t.dgA0, dgB = (zl | zh) ? t.dgB1 : t.dgB0;
+                    // Jacobi (off by default; the divisions cost nothing then): 1/diagonal of the air rows of
+                    // the pair, of conductor A rows and of U rows
+                    double jA = 0.0, jB = 0.0, jC = 0.0, jU = 0.0;
+                    if (JAC) { jA = 1.0 / dgA; jB = 1.0 / dgB; jC = 1.0 / mc.diag; jU = 1.0 / cf.diag_int; }
                     const double2 *m = pl3[sm_], *c = pl3[sc_], *z1 = pl3[sz_];
                     int ca = 0, cb = 0;
                     if (HAS_U) {
@@ -403,7 +414,7 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                             const double xm = in1<SAS>(tt - 1, A2, alpha), xp = in1<SAS>(tt + 2, A2, alpha);
                             const double ya = row7(czm, t.cym, cf.msx, dgA, t.cxpA, t.cyp, czp, m[a].x, ym.x, xm, c[a].x, c[a].y, yp.x, z1[a].x);
                             const double yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
-                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2, pxA, a, oA);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2, pxA, a, oA, jA, jB);
                         }
                     } else if (ca == 0x40 && cb == 0x40) {
                         // ---- both cells are interior conductor cells (all six neighbours conductor):
@@ -437,7 +448,7 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                             const double apB = (a == 0) ? xp : (a == 1) ? yp.y : z1[a].y;
                             suA = DADD(suA, DMUL(cf.ua_p[a], amA)); suA = DADD(suA, DMUL(cf.ua_m[a], apA));
                             suB = DADD(suB, DMUL(cf.ua_p[a], amB)); suB = DADD(suB, DMUL(cf.ua_m[a], apB));
-                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2, pxA, a, oA);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2, pxA, a, oA, jC, jC);
                         }
                         // U columns k-1, j-1, i-1, centre, i+1, j+1, k+1
                         suA = DADD(suA, DMUL(cf.msz, ugm.x)); suB = DADD(suB, DMUL(cf.msz, ugm.y));
@@ -447,7 +458,7 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                         suA = DADD(suA, DMUL(cf.msx, ugc.y)); suB = DADD(suB, DMUL(cf.msx, uxp));
                         suA = DADD(suA, DMUL(cf.msy, uyp.x)); suB = DADD(suB, DMUL(cf.msy, uyp.y));
                         suA = DADD(suA, DMUL(cf.msz, ugp.x)); suB = DADD(suB, DMUL(cf.msz, ugp.y));
-                        pair_out<MODE>(suA, suB, true, true, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2, pxU, 3, oU);
+                        pair_out<MODE>(suA, suB, true, true, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2, pxU, 3, oU, jU, jU);
                     } else {
                         // ---- conductor-surface cells / mixed pairs (never on a domain face): generic per-cell rows ----
                         const double2 ugm = ug3[sm_], ugc = ug3[sc_], ugp = ug3[sz_];
@@ -506,13 +517,14 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
                             } else {
                                 yb = row7(czm, t.cym, t.cxmB, dgB, cf.msx, t.cyp, czp, m[a].y, ym.y, c[a].x, c[a].y, xp, yp.y, z1[a].y);
                             }
-                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2, pxA, a, oA);
+                            pair_out<MODE>(ya, yb, true, true, a * G.segA + pA, c[a].x, c[a].y, aux[a], vs, a0, a1, a2, pxA, a, oA,
+                                           ca ? jC : jA, cb ? jC : jB);
                         }
                         // U rows
                         double sa_ = 0.0, sb_ = 0.0;
                         if (ca) sa_ = urow_u(cf, ca, ua[2].m1, ua[1].m1, ua[0].m1, ugc.x, ua[0].p1, ua[1].p1, ua[2].p1, suA);
                         if (cb) sb_ = urow_u(cf, cb, ub[2].m1, ub[1].m1, ub[0].m1, ugc.y, ub[0].p1, ub[1].p1, ub[2].p1, suB);
-                        pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2, pxU, 3, oU);
+                        pair_out<MODE>(sa_, sb_, ca != 0, cb != 0, pU, ugc.x, ugc.y, auxU, vs, a0, a1, a2, pxU, 3, oU, jU, jU);
                     }
                 }
                 if (MODE != MODE_PLAIN) {
@@ -532,7 +544,7 @@ __device__ __forceinline__ void tma_plane_loop(const TmaMaps &tm, const SlabGeom
 // bytes, all row rules; CPS = 1 CTA per SM gives it up to 255 registers, no spills) or lean
 // (7-point rows only, CPS >= 2).  Both launches of an SpMV share the reduction ticket: `expected`
 // = items of both, partial index = pbase + blockIdx.x.
-template <int MODE, int NSTAGE, bool HAS_U, int CPS>
+template <int MODE, int NSTAGE, bool HAS_U, int CPS, bool JAC>
 __global__ void __launch_bounds__(256, CPS)
 k_spmv_tma(const __grid_constant__ TmaMaps tm, const SlabGeom G, const Coef cf, const MatCoef mc,
            const WorkItem *__restrict__ items, const VecSet vs, const IterCtl ctl, double *partials, const int pstride,
@@ -591,7 +603,7 @@ k_spmv_tma(const __grid_constant__ TmaMaps tm, const SlabGeom G, const Coef cf, 
     __syncthreads();
 
     dd a0 = dd_zero(), a1 = dd_zero(), a2 = dd_zero();
-    tma_plane_loop<MODE, NSTAGE, HAS_U>(tm, G, cf, mc, vs, t, smem, full, cnt, a0, a1, a2, &pt, xf != 0);
+    tma_plane_loop<MODE, NSTAGE, HAS_U, JAC>(tm, G, cf, mc, vs, t, smem, full, cnt, a0, a1, a2, &pt, xf != 0);
 
     if (MODE != MODE_PLAIN) {
         const int pidx = pbase + blockIdx.x;

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libec3d_gpu.so")
 
 EXPORTS = [
     "sprsbcgstabwr_", "SPRSBCGSTABWR", "ec3d_bicgstabwr_csr", "ec3d_csr_cache_clear", "ec3d_nccl_unique_id",
-    "ec3d_create", "ec3d_destroy", "ec3d_sizes", "ec3d_assemble_csr", "ec3d_step", "ec3d_step_stage",
+    "ec3d_create", "ec3d_destroy", "ec3d_set_preconditioner", "ec3d_sizes", "ec3d_assemble_csr", "ec3d_step", "ec3d_step_stage",
     "ec3d_get_fields", "ec3d_set_fields", "ec3d_get_vtk_fields", "ec3d_get_source_cells", "ec3d_apply_operator",
     "ec3d_solve_host", "ec3d_bench_kernel", "ec3d_counters", "ec3d_timer_start", "ec3d_timer_stop", "ec3d_global_launch_count",
     "ec3d_last_error", "ec3d_version", "ec3d_partition_planes", "ec3d_plan_spmv_items",
@@ -81,6 +81,8 @@ def load() -> C.CDLL:
     L.ec3d_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     L.ec3d_destroy.restype = C.c_int
     L.ec3d_destroy.argtypes = [vp]
+    L.ec3d_set_preconditioner.restype = C.c_int
+    L.ec3d_set_preconditioner.argtypes = [vp, i32]
     L.ec3d_sizes.restype = C.c_int
     L.ec3d_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
     L.ec3d_assemble_csr.restype = C.c_int
@@ -231,6 +233,10 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def set_preconditioner(self, kind: int):
+        """0 = none (the reference's algorithm, default), 1 = Jacobi (changes iterates)."""
+        _check(load().ec3d_set_preconditioner(self._h, int(kind)))
 
     # -- gen_sparse_matrix ---------------------------------------------------------------------
     def assemble_csr(self) -> dict:

@@ -113,6 +113,12 @@ int ec3d_nccl_unique_id(void *id128);
 int ec3d_create(const ec3d_config *cfg, ec3d_handle **out);
 int ec3d_destroy(ec3d_handle *h);
 
+/* Optional preconditioning of the resident solver.  kind 0 = none (default: the
+ * reference's algorithm, solvers.f90:3-50), 1 = Jacobi: BiCGSTABwr on D^-1 A x = D^-1 b with D the matrix
+ * diagonal (EC3D.f90:533-663).  It changes the iterates and iteration counts, so parity with the reference
+ * only holds for kind 0.  With nranks > 1 every rank must make the same call. */
+int ec3d_set_preconditioner(ec3d_handle *h, int32_t kind);
+
 /* Sizes: n = nCellsGlob (global), and this rank's slab [k0,k1) (0-based planes) and owned unknown
  * count. */
 int ec3d_sizes(const ec3d_handle *h, int64_t *nCells, int64_t *nCells0, int64_t *nCellsGlob,

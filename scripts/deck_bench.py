@@ -17,7 +17,10 @@ for deck in ("compare_to_Elmer", "ec_src_move_hole", "LIM"):
         t0 = time.perf_counter(); it = h.step(f, v); dt = time.perf_counter() - t0
         its.append(it); ms.append(1e3 * dt)
     c = h.counters()
+    kern = {name: round(1e3 * h.bench_kernel(which, 5, 50), 2) for which, name, *_ in lib.KERNELS}   # us per launch
+    kern["whole_iteration_enqueued"] = round(1e3 * h.bench_kernel(5, 5, 50), 2)
     print(json.dumps({"deck": deck, "n": p.nCellsGlob, "steps": nsteps, "iters": its,
                       "ms_per_step_mean_after_first": round(float(np.mean(ms[1:])), 3),
-                      "us_per_iteration": round(1e3 * float(np.sum(ms[1:])) / max(sum(its[1:]), 1), 2)}))
+                      "us_per_iteration": round(1e3 * float(np.sum(ms[1:])) / max(sum(its[1:]), 1), 2),
+                      "us_per_kernel_launch": kern}))
     h.close()

@@ -378,3 +378,36 @@ def test_dropin_cache_sees_reassembled_matrix(gpu_lib, oracle_mod, plates):
     assert it2 == it2o and rel(x2, x2o) < REL_L2_TOL
     assert it1 == it2 and rel(2.0 * x2, x1) < 1e-12     # (2A) x = b  ->  x = x1 / 2 (scaling by 2 is exact)
     gpu_lib.load().ec3d_csr_cache_clear()
+
+
+def test_optional_jacobi_preconditioner(gpu_lib, oracle_mod, plates):
+    """Jacobi scaling is OFF by default (parity above); switched on, BiCGSTABwr runs on
+    D^-1 A x = D^-1 b: it must converge in the scaled residual norm, and switching it off again must
+    restore the reference's iterates bit for bit."""
+    p = plates["A"]
+    run, b = _rhs_of_first_step(oracle_mod, p)
+    A = run.A
+    n = p.nCellsGlob
+    # diagonal of the assembled matrix
+    rows = np.repeat(np.arange(n), np.diff(A.irow))
+    diag = np.zeros(n)
+    on_diag = (A.jcol - 1) == rows
+    diag[rows[on_diag]] = A.valA[on_diag]
+    assert np.all(diag != 0)
+    h = gpu_lib.Handle(p, device=0)
+    x0 = np.zeros(n)
+    it0 = h.solve(b, x0)
+    h.set_preconditioner(1)
+    x1 = np.zeros(n)
+    it1 = h.solve(b, x1)
+    r = b - h.apply_operator(x1)
+    scaled = np.linalg.norm(r / diag) / np.linalg.norm(b / diag)
+    print(f"plate(32) step-1 system: {it0} iterations unpreconditioned, {it1} with Jacobi; scaled residual {scaled:.2e}")
+    assert 0 < it1 <= p.itmax and scaled < 1.05 * p.tolerance
+    assert rel(x1, x0) < 0.2                     # same solution up to the (loose) tolerance
+    h.set_preconditioner(0)
+    x2 = np.zeros(n)
+    assert h.solve(b, x2) == it0 and np.array_equal(x2, x0)
+    with pytest.raises(gpu_lib.Ec3dError):
+        h.set_preconditioner(7)
+    h.close()
