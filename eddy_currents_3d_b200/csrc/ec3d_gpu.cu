@@ -700,6 +700,17 @@ static int h_allreduce(ec3d_handle *h, int slot, int count)
 
 static int scan_i32_to_i64(cudaStream_t st, const int *in, long long *out, long long n, long long *total_host, long long &launches);
 
+// A wait on a neighbour's epoch flag gave up (ec3d_comm.cuh: ~30 s): the kernels that followed ran on
+// stale halos / partial sums.  Every entry point that launches exchanging kernels reports it.
+static int comm_check(ec3d_handle *h)
+{
+    if (!h->p2p || !h->d_cl) return EC3D_OK;
+    int err = 0;
+    CUDA_TRY(cudaMemcpy(&err, &h->d_cl->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) { ec3d_set_error("peer-to-peer exchange timed out waiting for a neighbour rank (results are invalid)"); return EC3D_ERR_NCCL; }
+    return EC3D_OK;
+}
+
 // Ring depth per (mode, item kind, CTAs per SM).  Lean items (no conductor cells): 2 CTAs / SM; the
 // modes that also stream r0 / b through L1 (AP, INIT) measure faster with 3 stages (more of the 228 KB
 // left as L1), PLAIN with 4; MODE_SAS stages two inputs (32 KB per stage).  Conductor items: EC3D_CCPS
@@ -888,49 +899,15 @@ static void plan_spmv_items(const SlabGeom &G, int zc, bool plane_major, std::ve
         std::stable_sort(items.begin(), items.end(), [](const WorkItem &a, const WorkItem &b) { return a.kb < b.kb; });
 }
 
-// Planes per item.  Long items amortise the 2 halo planes and the pipeline fill, short ones fill the
-// last wave of CTAs evenly; which wins depends on how many (tile column x z) items the slab has relative
-// to the 2 x 148 resident CTAs.  So the host SIMULATES the launch for a few candidate lengths -- list
-// scheduling of the planned items (conductor items first, about 2.2x the cost per plane, measured) on
-// 296 CTA slots -- and keeps the length with the best useful-work / (slots x makespan).  On plate(512)
-// every candidate is within 2 %; on plate(256) and on the 64-plane slabs of an 8-GPU run the spread is
-// 0.84 ... 0.98 (scripts: see DESIGN.md section 3.1).
-static double simulate_items(const std::vector<WorkItem> &items)
-{
-    const int slots = 2 * 148;
-    std::vector<double> heap(slots, 0.0);               // min-heap of slot finish times
-    auto cmp = [](double a, double b) { return a > b; };
-    double useful = 0.0;
-    auto run = [&](bool cond) {
-        for (const WorkItem &w : items) {
-            if ((w.has_u != 0) != cond) continue;
-            const double per = w.has_u ? 2.2 : 1.0;
-            const int nz = w.ke - w.kb;
-            std::pop_heap(heap.begin(), heap.end(), cmp);
-            heap.back() += per * (nz + 2.0);            // ~1 plane for the 2 halo planes (loads only) + ~1 of pipeline fill
-            std::push_heap(heap.begin(), heap.end(), cmp);
-            useful += per * nz;
-        }
-    };
-    run(true); run(false);
-    const double makespan = *std::max_element(heap.begin(), heap.end());
-    return makespan > 0.0 ? useful / (slots * makespan) : 0.0;
-}
-
+// Planes per item, measured (profiles/r02_item_length_sweep.md): 32 on large grids -- plate(512): A*p 0.94 /
+// fused A*s 0.89 of the copy peak at 32 vs 0.92 / 0.84 at 64 and 0.93 / 0.88 at 24; plate(256): 32 is the
+// optimum as well.  Small grids (the shipped decks: everything is L2 resident, a plane costs ~1.5 us of
+// latency) want as many short items as there are CTA slots: one wave of 2 x 148 CTAs.
 static int default_item_planes(const SlabGeom &G)
 {
-    static const int cand[] = {12, 16, 20, 24, 28, 32, 40, 48, 64};
-    int best = 48;
-    double best_eff = -1.0;
-    std::vector<WorkItem> items;
-    for (int zc : cand) {
-        if (zc > std::max(4, G.nzl)) continue;
-        plan_spmv_items(G, zc, true, items);
-        const double e = simulate_items(items);
-        if (e > best_eff + 1e-9) { best_eff = e; best = zc; }
-    }
-    if (best_eff < 0.0) best = std::max(2, std::min(48, G.nzl));
-    return best;
+    const long long tx = (G.sdx + tma::TX - 1) / tma::TX, ty = (G.sdy + tma::TY - 1) / tma::TY;
+    const long long one_wave = ((long long)G.nzl * tx * ty + 2 * 148 - 1) / (2 * 148);
+    return (int)std::min<long long>(32, std::max<long long>(2, one_wave));
 }
 
 extern "C" int ec3d_plan_spmv_items(int32_t sdx, int32_t sdy, int32_t k0, int32_t k1, const int32_t box[6], int32_t zc,
@@ -1468,7 +1445,8 @@ static int create_impl(const ec3d_config *cfg, ec3d_handle *h)
     // ---- NCCL ----
     if (h->nranks > 1) {
         if (!cfg->nccl_id) { ec3d_set_error("nccl_id required for nranks > 1"); return EC3D_ERR_ARG; }
-        if (G.nzl < 2) { ec3d_set_error("each slab needs at least 2 planes"); return EC3D_ERR_ARG; }
+        for (int r = 0; r < h->nranks; ++r)       // same answer on every rank: nobody is left alone in a collective
+            if (kstart[r + 1] - kstart[r] < 2) { ec3d_set_error("each slab needs at least 2 planes"); return EC3D_ERR_ARG; }
         ncclUniqueId id;
         memcpy(&id, cfg->nccl_id, 128);
         NCCL_TRY(ncclCommInitRank(&h->comm, h->nranks, id, h->rank));
@@ -1603,7 +1581,7 @@ extern "C" int ec3d_set_fields(ec3d_handle *h, const double *Uaf, const double *
     if (Uaf && (rc = copy_in(h, h->Uaf, Uaf))) return rc;
     if (Jaf && (rc = copy_in(h, h->Jaf, Jaf))) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->st));
-    return EC3D_OK;
+    return comm_check(h);
 }
 
 extern "C" int ec3d_get_vtk_fields(ec3d_handle *h, float *field_A, float *field_eddy, float *field_source, float *field_B,
@@ -1631,7 +1609,7 @@ extern "C" int ec3d_get_vtk_fields(ec3d_handle *h, float *field_A, float *field_
     }
     CUDA_TRY(cudaStreamSynchronize(h->st));
     CUDA_TRY(cudaGetLastError());
-    return EC3D_OK;
+    return comm_check(h);
 }
 
 extern "C" int ec3d_get_source_cells(ec3d_handle *h, int32_t *cells)
@@ -1656,7 +1634,7 @@ extern "C" int ec3d_apply_operator(ec3d_handle *h, const double *x, double *y)
     if ((rc = copy_out(h, y, h->tmpy))) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->st));
     CUDA_TRY(cudaGetLastError());
-    return EC3D_OK;
+    return comm_check(h);
 }
 
 extern "C" int ec3d_solve_host(ec3d_handle *h, const double *b, double *x, int32_t *iter)
@@ -1676,7 +1654,7 @@ extern "C" int ec3d_solve_host(ec3d_handle *h, const double *b, double *x, int32
     if (rc) return rc;
     if ((rc = copy_out(h, x, h->tmpy))) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->st));
-    return EC3D_OK;
+    return comm_check(h);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1737,12 +1715,7 @@ static int stage_solve(ec3d_handle *h, int32_t *iter)
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev[3], h->st));
     if (iter) *iter = it;
-    if (h->p2p) {
-        int err = 0;
-        CUDA_TRY(cudaMemcpy(&err, &h->d_cl->error, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) { ec3d_set_error("peer-to-peer exchange timed out waiting for a neighbour"); return EC3D_ERR_NCCL; }
-    }
-    return EC3D_OK;
+    return comm_check(h);
 }
 
 static int stage_rhs_post(ec3d_handle *h)
@@ -1998,5 +1971,5 @@ extern "C" int ec3d_bench_kernel(ec3d_handle *h, int32_t which, int32_t warm, in
     CUDA_TRY(cudaMemsetAsync(s.R, 0, (size_t)G.ltot * 8 * sizeof(double), h->st));
     CUDA_TRY(cudaStreamSynchronize(h->st));
     CUDA_TRY(cudaGetLastError());
-    return EC3D_OK;
+    return comm_check(h);
 }

@@ -72,12 +72,43 @@ def _tand(x: float) -> float:
     return math.tan(math.radians(math.fmod(x, 360.0)))
 
 
+class _EvalError(Exception):
+    """An evaluation error of the reference's evalf (EvalErrType > 0): the WHOLE expression evaluates to 0
+    (m_fparser.f90:182,187,210-214: `res=zero; RETURN`), not just the failing sub-expression."""
+
+
+def _lg(y):
+    if y <= 0.0:                       # m_fparser.f90:187  EvalErrType=3
+        raise _EvalError("lg of a non-positive number")
+    return math.log10(y)
+
+
+def _ln(y):                            # m_fparser.f90:189: plain LOG, no check
+    return math.log(y) if y > 0.0 else (-math.inf if y == 0.0 else math.nan)
+
+
+def _sqrt(y):                          # m_fparser.f90:190: plain DSQRT, no check
+    return math.sqrt(y) if y >= 0.0 else math.nan
+
+
+def _asin(y):
+    if y < -1.0 or y > 1.0:            # m_fparser.f90:210-211  EvalErrType=4
+        raise _EvalError("asin argument outside [-1, 1]")
+    return math.asin(y)
+
+
+def _acos(y):
+    if y < -1.0 or y > 1.0:            # m_fparser.f90:213-214  EvalErrType=4
+        raise _EvalError("acos argument outside [-1, 1]")
+    return math.acos(y)
+
+
 _FUNCS = {
     "abs": abs,
     "exp": math.exp,
-    "lg": math.log10,
-    "ln": math.log,
-    "sqrt": math.sqrt,
+    "lg": _lg,
+    "ln": _ln,
+    "sqrt": _sqrt,
     "sh": math.sinh,
     "ch": math.cosh,
     "th": lambda y: math.sinh(y) / math.cosh(y),
@@ -88,8 +119,8 @@ _FUNCS = {
     "sin": math.sin,
     "cos": math.cos,
     "tg": math.tan,
-    "asin": math.asin,
-    "acos": math.acos,
+    "asin": _asin,
+    "acos": _acos,
     "impls": lambda y: 1.0 if y > 0.0 else 0.0,
     "impl2": lambda y: 1.0 if y >= 0.0 else -1.0,
     "pos": lambda y: y if y > 0.0 else 0.0,
@@ -155,7 +186,7 @@ def _eval(F: str, b: int, e: int, var: Dict[str, float]) -> float:
                     return lhs * rhs
                 if op == "/":
                     if rhs == 0.0:
-                        return 0.0  # EvalErrType=1, res=zero (m_fparser.f90:180)
+                        raise _EvalError("division by zero")   # EvalErrType=1, res=zero; RETURN (m_fparser.f90:182)
                     return lhs / rhs
                 return lhs ** rhs
     b2 = b + 1 if F[b] == "-" else b
@@ -173,7 +204,10 @@ def evalf(expr: str, var: Dict[str, float]) -> float:
     F = expr.replace("**", "^").replace(" ", "").replace("\t", "")
     if not F:
         raise ValueError("empty expression")
-    return _eval(F, 0, len(F) - 1, var)
+    try:
+        return _eval(F, 0, len(F) - 1, var)
+    except _EvalError:
+        return 0.0
 
 
 _PREFIXES = [("M", None), ("K", 1e3), ("U", 1e-6), ("N", 1e-9), ("P", None), ("G", 1e9), ("T", 1e12),

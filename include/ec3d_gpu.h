@@ -110,6 +110,13 @@ typedef struct {
 
 int ec3d_nccl_unique_id(void *id128);
 
+/* With nranks > 1 the following calls are COLLECTIVE: every rank must make them in the same order with
+ * compatible arguments, or the ranks' exchange epochs desynchronise and the waiting side gives up after
+ * about 30 s with EC3D_ERR_NCCL: ec3d_create, ec3d_step / ec3d_step_stage (stages 1 and 2), ec3d_set_fields
+ * (one exchange per non-NULL field), ec3d_apply_operator, ec3d_solve_host, ec3d_get_vtk_fields with
+ * field_B != NULL, ec3d_set_preconditioner, ec3d_bench_kernel, ec3d_destroy.  ec3d_get_fields,
+ * ec3d_get_source_cells, ec3d_counters and the timers are local. */
+
 int ec3d_create(const ec3d_config *cfg, ec3d_handle **out);
 int ec3d_destroy(ec3d_handle *h);
 

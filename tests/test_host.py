@@ -39,6 +39,19 @@ def test_fparser_operator_split():
     assert evalf("1.5E+2+A", v) == 153.0
 
 
+def test_fparser_evaluation_errors_zero_the_whole_expression():
+    """m_fparser.f90:182,187,210-214: on division by zero, lg(<=0), asin/acos outside [-1,1] evalf sets
+    EvalErrType and returns ZERO for the whole expression (`res=zero; RETURN`); sqrt / ln are unchecked."""
+    import math
+    from eddy_currents_3d_b200.fparser import evalf
+    assert evalf("1+1/0", {}) == 0.0                 # not 1
+    assert evalf("5*(2+lg(0))", {}) == 0.0
+    assert evalf("3-asin(2)", {}) == 0.0 and evalf("3-acos(-1.5)", {}) == 0.0
+    assert evalf("1+A/B", {"A": 1.0, "B": 0.0}) == 0.0
+    assert evalf("1+1/4", {}) == 1.25
+    assert math.isnan(evalf("sqrt(0-1)", {})) and evalf("ln(0)", {}) == -math.inf
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference decks not present")
 @pytest.mark.parametrize("deck", DECKS)
 def test_vxc_loader_matches_golden(deck, deck_problems):
