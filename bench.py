@@ -229,8 +229,14 @@ def main():
     scal = [p.source_scalars(s * p.dt) for s in range(nsteps_total)]
     # pinned host buffers: per-step scalars in, full fields out
     fsrc = torch.zeros(max(p.numfun, 1), dtype=torch.float64).pin_memory()
-    U_host = torch.empty(n, dtype=torch.float64).pin_memory()
-    J_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    # full-length host fields in the reference layout (every rank fills its owned entries).  Pinned, unless
+    # all ranks together would pin more than 64 GB of host memory (plate(768) on 8 ranks): then pageable,
+    # lazily committed memory -- only the owned ranges are ever touched
+    pin_fields = 16.0 * n * world < 64e9
+    U_host = torch.empty(n, dtype=torch.float64)
+    J_host = torch.empty(n, dtype=torch.float64)
+    if pin_fields:
+        U_host, J_host = U_host.pin_memory(), J_host.pin_memory()
 
     def do_step(s):
         fsrc[:p.numfun] = torch.from_numpy(scal[s][0])
@@ -326,7 +332,7 @@ def main():
                    "create_s": t_create},
         "e2e": {"value": e2e_step, "unit": UNIT, "h2d_bytes_per_step": 8 * (p.numfun + p.numMech),
                 "d2h_bytes_per_step": 16 * n_own + 16, "iters_per_step": iters,
-                "same_steps_as_value": True},
+                "same_steps_as_value": True, "host_fields_pinned": bool(pin_fields)},
         "gpu_launches": int(c1["launches"] - c0["launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": kd["GBps"], "peak": peak, "unit": "GB/s", "frac": kd["frac"],

@@ -45,6 +45,8 @@ CASES = [
 def test_ranks_equal_one_gpu_and_oracle(nranks, what, comm, kstart):
     if _ngpus() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
+    if nranks < int(os.environ.get("EC3D_TEST_MIN_RANKS", "0")):
+        pytest.skip("EC3D_TEST_MIN_RANKS")
     env = dict(os.environ, EC3D_COMM=comm)
     if kstart:
         env["EC3D_KSTART"] = kstart
