@@ -124,6 +124,50 @@ def oracle_ms_per_iter(grid: int, iters: int):
     return 1e3 * dt / max(it, 1), it, t_asm, p.nCells
 
 
+def decks_section(nsteps: int = 10):
+    """The three shipped decks (the only configurations the reference itself can run), first `nsteps`
+    timesteps, measured for real -- no extrapolation: (a) GPU-resident stepping through ec3d_step; (b) the
+    strict drop-in: the reference's time loop (CPU, oracle port standing in for the Fortran host) calling
+    sprsbcgstabwr_ on its own CSR arrays with host buffers, solver calls timed; (c) the CPU baseline: the
+    oracle port end to end, 1 thread, on this host.  ms per step = mean over steps 1..nsteps-1."""
+    from eddy_currents_3d_b200 import lib
+    from eddy_currents_3d_b200.problem import load_problem_npz
+    from oracle import oracle
+    out = {}
+    for deck in ("compare_to_Elmer", "ec_src_move_hole", "LIM"):
+        p = load_problem_npz(os.path.join(ROOT, "tests", "golden", deck + ".npz"))
+        scal = [p.source_scalars(s * p.dt) for s in range(nsteps)]
+        h = lib.Handle(p, device=0)
+        its, ms = [], []
+        for s in range(nsteps):
+            t0 = time.perf_counter(); its.append(h.step(*scal[s])); ms.append(1e3 * (time.perf_counter() - t0))
+        h.close()
+        gpu = {"ms_per_step": float(np.mean(ms[1:])), "iters": its, "us_per_iteration": 1e3 * float(np.sum(ms[1:])) / max(sum(its[1:]), 1)}
+        A = oracle.Assembled(p)
+        tsolve = []
+
+        def gpu_solver(valA, irow, jcol, n, b, x, tol, itmax):
+            t0 = time.perf_counter()
+            it = lib.sprsBCGstabWR(valA, irow, jcol, n, b, x, tol, itmax)
+            tsolve.append(1e3 * (time.perf_counter() - t0))
+            return it
+        host = oracle.OracleRun(p, A, solver=gpu_solver)
+        its_d = [host.step(*scal[s]) for s in range(nsteps)]
+        lib.load().ec3d_csr_cache_clear()
+        drop = {"solver_ms_per_step": float(np.mean(tsolve[1:])), "iters": its_d,
+                "us_per_iteration": 1e3 * float(np.sum(tsolve[1:])) / max(sum(its_d[1:]), 1),
+                "note": "CSR SpMV on the reference's arrays; b and x cross PCIe every call; first call uploads the matrix"}
+        cpu = oracle.OracleRun(p, A)
+        its_c, ms_c = [], []
+        for s in range(nsteps):
+            t0 = time.perf_counter(); its_c.append(cpu.step(*scal[s])); ms_c.append(1e3 * (time.perf_counter() - t0))
+        out[deck] = {"unknowns": p.nCellsGlob, "steps": nsteps, "gpu_resident": gpu, "gpu_dropin": drop,
+                     "cpu_oracle_1thread": {"ms_per_step": float(np.mean(ms_c[1:])), "iters": its_c,
+                                            "ms_per_iteration": float(np.sum(ms_c[1:])) / max(sum(its_c[1:]), 1)},
+                     "speedup_resident_vs_cpu": float(np.mean(ms_c[1:]) / np.mean(ms[1:]))}
+    return out
+
+
 def recorded_iters(grid: int, first: int = 0, count: int = 0):
     """Mean BiCGSTABwr iterations per timestep of the GPU arm on plate(grid), steps [first, first+count)
     when the record has them (the iteration counts are deterministic: same for every GPU count)."""
@@ -188,6 +232,7 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=15)
     ap.add_argument("--cpu-grid", type=int, default=160, help="grid of the in-line cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-decks", action="store_true", help="skip the shipped-deck section (N = 1 only)")
     ap.add_argument("--record-iters", action="store_true", help="write profiles/bench_iters.json")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -303,6 +348,8 @@ def main():
         byt = bpn * nn + bpc * cc
         kernels[name] = {"ms": ms_k, "bytes": byt, "GBps": byt / (ms_k * 1e-3) / 1e9, "frac": byt / (ms_k * 1e-3) / 1e9 / peak,
                          "slowest_rank": r, "replaces": what}
+        if world > 1:
+            kernels[name]["ms_by_rank"] = [round(float(v), 4) for v in allk[:, q]]
     it_bytes_rank0 = 152.0 * n_own + 10.0 * nC_own
     # whole iteration against SURVEY 8d's UNCHANGED figure (19 passes + 2 map reads), slab of the largest rank
     it_bytes = max(152.0 * float(a[-2]) + 10.0 * float(a[-1]) for a in allk)
@@ -347,6 +394,7 @@ def main():
                                        "over the measured time per BiCGSTABwr iteration of the timed solves; the kernels "
                                        "make fewer passes than that figure assumes (see DESIGN.md section 3)"},
         "kernels": kernels,
+        "owned_unknowns_by_rank": [int(a[-2]) for a in allk],
         "sum_kernel_ms": float(sum(k["ms"] for k in kernels.values())),
     }
     if world == 1:
@@ -379,8 +427,13 @@ def main():
                 "ms_per_iteration_sample": ms_it}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
-    print(json.dumps(line), flush=True)
     h.close()
+    if world == 1 and not args.no_decks and not args.no_cpu:
+        try:
+            line["decks"] = decks_section()
+        except Exception as e:  # noqa: BLE001
+            line["decks"] = {"error": str(e)}
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -150,7 +150,6 @@ __device__ __forceinline__ void reduce_epilogue(dd a0, dd a1, dd a2, double *par
 {
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     const int nthr = blockDim.x * blockDim.y * blockDim.z;
-    if (xc.pt) __threadfence_system();          // every thread: its stores into the neighbours' memory
     dd s0 = block_sum(a0, sh);
     dd s1 = dd_zero(), s2 = dd_zero();
     if (NRED > 1) s1 = block_sum(a1, sh);
@@ -160,7 +159,11 @@ __device__ __forceinline__ void reduce_epilogue(dd a0, dd a1, dd a2, double *par
         partials[2 * pidx] = s0.hi; partials[2 * pidx + 1] = s0.lo;
         if (NRED > 1) { partials[2 * (pstride + pidx)] = s1.hi; partials[2 * (pstride + pidx) + 1] = s1.lo; }
         if (NRED > 2) { partials[2 * (2 * pstride + pidx)] = s2.hi; partials[2 * (2 * pstride + pidx) + 1] = s2.lo; }
-        if (xc.pt) __threadfence_system();      // this block's peer stores (fused halo push) before the ticket
+        // thread 0 fences for the whole block: the barriers inside block_sum order every thread's stores
+        // (own partials, fused halo push into the neighbours' memory) before this fence, and fences are
+        // cumulative -- the pattern of a grid-wide barrier.  One system-scope fence per block, not per
+        // thread (256 x thousands of blocks of membar.sys cost ~0.1 ms per SpMV on 8 GPUs).
+        if (xc.pt) __threadfence_system();
         else __threadfence();
         ticket_s = atomicAdd(&sc->counter, 1u);
     }
@@ -816,8 +819,7 @@ k_xr_update_tma(const SlabGeom G, double *__restrict__ X, const double *__restri
 // all blocks of the p-update have fenced their peer stores: the last one tells the neighbours
 __device__ __forceinline__ void p_push_done(const PeerTable &pt, CommLocal *cl)
 {
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                                   // (thread 0's fence below covers the block, see reduce_epilogue)
     if (threadIdx.x != 0) return;
     __threadfence_system();
     if (atomicAdd(&cl->ticket_p, 1u) != gridDim.x - 1) return;

@@ -225,10 +225,13 @@ class Assembled:
 class OracleRun:
     """The reference's main program (EC3D.f90:93-455) over the oracle subroutines."""
 
-    def __init__(self, problem, assembled: Optional[Assembled] = None, exact_dots: bool = False):
+    def __init__(self, problem, assembled: Optional[Assembled] = None, exact_dots: bool = False, solver=None):
         p = problem
         self.p = p
         self.exact_dots = exact_dots          # True: the bridge solver instead of the reference's reductions
+        # solver(valA, irow, jcol, n, b, x, tolerance, itmax) -> iter: stands in for the CALL at EC3D.f90:408
+        # (bench.py times the GPU drop-in sprsbcgstabwr_ inside the reference's own time loop this way)
+        self.solver = solver
         self.A = assembled if assembled is not None else Assembled(p)
         if self.A.rc != 0:
             raise RuntimeError(f"gen_sparse_matrix: reference would STOP (rc={self.A.rc}, "
@@ -285,7 +288,9 @@ class OracleRun:
         L.orc_rhs_pre(C.byref(self.A.grid), C.byref(self.cond), C.byref(self.A.csr), _p(self.Uaf), _p(self.Jaf))
         self.rhs = self.Jaf.copy()
         it = 0
-        if solve and self.exact_dots:
+        if solve and self.solver is not None:
+            it = self.solver(self.A.valA, self.A.irow, self.A.jcol, p.nCellsGlob, self.Jaf, self.Uaf, p.tolerance, p.itmax)
+        elif solve and self.exact_dots:
             it = bicgstabwr_exact_dots(self.A.valA, self.A.irow, self.A.jcol, self.Jaf, self.Uaf, p.tolerance, p.itmax, p)
         elif solve:
             it = bicgstabwr(self.A.valA, self.A.irow, self.A.jcol, self.Jaf, self.Uaf, p.tolerance, p.itmax)
