@@ -6,6 +6,9 @@ contiguous U range (U unknowns are numbered in k,j,i order for a single conducto
 over the owned rows reads, besides owned entries, exactly: one plane of each A component below and
 above, and the U unknowns of the two planes below and above (one-sided z-gradients reach two cells,
 EC3D.f90:697-706).
+
+Used by the tests only (tests/test_distributed_cpu.py checks the halo / ownership bookkeeping with a
+world-size-2 gloo group on the CPU); the product path keeps its own copy of this layout in C++.
 """
 from __future__ import annotations
 
