@@ -1951,8 +1951,9 @@ extern "C" int ec3d_bench_kernel(ec3d_handle *h, int32_t which, int32_t warm, in
         return EC3D_OK;
     };
     k_bench_scalars<<<1, 1, 0, h->st>>>(s.sc, s.iter_base);
-    // deterministic non-trivial data: fill the Krylov vectors from a splitmix-like pattern
-    k_fill<<<148 * 4, 256, 0, h->st>>>(s.R, G.ltot * 6, 0.5);
+    // deterministic data with realistic bit activity: the Krylov vectors and the stand-in for x get splitmix64 values
+    k_fill_random<<<148 * 4, 256, 0, h->st>>>(s.R, G.ltot * 6, 0x5EEDull);
+    k_fill_random<<<148 * 4, 256, 0, h->st>>>(h->tmpx, G.ltot, 0xEC3Dull);
     for (int q = 0; q < warm; ++q) { int rc = one(); if (rc) return rc; k_bench_scalars<<<1, 1, 0, h->st>>>(s.sc, s.iter_base); }
     CUDA_TRY(cudaStreamSynchronize(h->st));
     float total = 0.f;
