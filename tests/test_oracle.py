@@ -290,3 +290,17 @@ def test_exact_dot_bridge_is_the_same_algorithm(oracle_mod):
     with pytest.raises(RuntimeError):
         q = plate(32, "A"); q.sdx = 31
         oracle_mod.bicgstabwr_exact_dots(a.A.valA, a.A.irow, a.A.jcol, a.Jaf, a.Uaf.copy(), 5e-3, 10, q)
+
+
+def test_committed_bridge_record_reproduces(oracle_mod):
+    """tests/golden/parity_bridge.json (the record the GPU hash tests compare with) is what the bridge
+    solver produces: re-run plate(32) and compare iteration counts and SHA-256 of the fields."""
+    import hashlib
+    from eddy_currents_3d_b200 import plate
+    rec = json.load(open(os.path.join(GOLDEN, "parity_bridge.json")))["32"]["free"]
+    p = plate(32, "A")
+    run = oracle_mod.OracleRun(p, exact_dots=True)
+    for r in rec:
+        assert run.step() == r["it_bridge"]
+        assert hashlib.sha256(run.Uaf.tobytes()).hexdigest() == r["sha256_U_bridge"]
+        assert hashlib.sha256(run.Jaf.tobytes()).hexdigest() == r["sha256_J_bridge"]
