@@ -84,7 +84,7 @@ def _committed():
     return json.load(open(path)) if os.path.exists(path) else {}
 
 
-@pytest.mark.parametrize("n", [32, 64, 128, 256])
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 384])
 def test_gpu_matches_committed_bridge_hashes(gpu_lib, n):
     """P1 at the sizes where running the oracle inside the GPU test would take many minutes: the bridge
     ran on the CPU (scripts/parity_table.py) and its iteration counts and SHA-256 of Uaf / Jaf per
