@@ -14,7 +14,7 @@ Three statements, see tests/parity_util.py for the four arms:
  P3  free-running steps: iteration counts and fields are reported; they are asserted only against
      the oracle's own spread (the oracle run with pairwise reductions moves as far or further).
 
-Numbers at N = 32 / 64 / 128 are tabulated by scripts/parity_table.py -> profiles/r02_parity_table.md.
+Numbers at N = 32 ... 384 are tabulated by scripts/parity_table.py -> profiles/r02_parity_table.md.
 """
 import hashlib
 import json
