@@ -47,6 +47,9 @@ def test_ranks_equal_one_gpu_and_oracle(nranks, what, comm, kstart):
         pytest.skip(f"needs {nranks} GPUs")
     if nranks < int(os.environ.get("EC3D_TEST_MIN_RANKS", "0")):
         pytest.skip("EC3D_TEST_MIN_RANKS")
+    only = os.environ.get("EC3D_TEST_CASES")          # e.g. "0,1,4": indices into CASES (GPU-minute budgets)
+    if only and str(CASES.index((nranks, what, comm, kstart))) not in only.split(","):
+        pytest.skip("EC3D_TEST_CASES")
     env = dict(os.environ, EC3D_COMM=comm)
     if kstart:
         env["EC3D_KSTART"] = kstart
